@@ -1,0 +1,167 @@
+/* include/tracer_rq.h -- C-ABI of the B200-native ray-query engine ("trq").
+ *
+ * Drop-in boundary for the ONE hot path of iaomw/Tracer this repository replaces: the
+ * RT_Metal ray query. Everything crossing this boundary is a plain pointer + size in the
+ * reference's own byte layouts; there are no torch / C++ types in any signature.
+ *
+ *   reference interface                                      replaced by
+ *   -------------------------------------------------------  ---------------------------
+ *   struct Primitive (6 device pointers)                     trq_scene_desc
+ *       RT_Metal/Metal/Render.hh:122-130
+ *   newBufferWithBytes idx / tri / bvh  (host->device seam)  trq_scene_create
+ *       RT_Metal/Tracer/AAPLRenderer.mm:217-231,614-624
+ *   argumentEncoderPri setBuffer x6                          (held inside trq_scene)
+ *       RT_Metal/Tracer/AAPLRenderer.mm:712-720
+ *   bool Scene::hit(ray, hitRecord, test_t, any)             trq_trace (one call = a batch of rays)
+ *       RT_Metal/Metal/Render.hh:132-252
+ *   struct Ray   RT_Metal/Metal/Ray.hh:10-33                 trq_ray  (first 32 B of Ray; tmax = test_t)
+ *   struct HitRecord  RT_Metal/Metal/HitRecord.hh:9-30       trq_hit (compact, + primitive id) and
+ *                                                            trq_hit_record via trq_expand_hits
+ *   BVH::buildNode / BVH::buildTree (host)                   trq_bvh_build_node(s) / trq_bvh_build_tree
+ *       RT_Metal/Metal/BVH.hh:246-314
+ *
+ * Scene arrays use the reference byte layouts (Metal / Apple-simd rules, float3 = 16 B):
+ *   BVH 64 B (BVH.hh:15-22), AABB 32 B (AABB.hh:7-9), TriangleVertex 32 B (Triangle.hh:12-18),
+ *   Sphere 272 B (Sphere.hh:6-15), Square 272 B (Square.hh:12-27), Cube 240 B (Cube.hh:6-13).
+ *
+ * Results are bit-identical to the reference's Scene::hit evaluated in strict IEEE fp32
+ * (hit flag, t, primitive id, barycentrics): same per-ray visit order, same arithmetic.
+ *
+ * Error convention: every call returns TRQ_OK (0) or a negative trq_status; no C++
+ * exception crosses the ABI; trq_last_error_string() describes the last failure on the
+ * calling thread. There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with TRQ_ERR_NO_DEVICE.
+ */
+#ifndef TRACER_RQ_H
+#define TRACER_RQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRQ_VERSION 100  /* 0.1.0 */
+
+typedef enum trq_status {
+    TRQ_OK            =  0,
+    TRQ_ERR_INVALID   = -1,   /* NULL / inconsistent argument */
+    TRQ_ERR_LAYOUT    = -2,   /* scene arrays violate the reference layout contract (bad index, cycle, ...) */
+    TRQ_ERR_DEPTH     = -3,   /* interior depth > 32: the reference's 32-bit trail cannot represent it (Render.hh:140) */
+    TRQ_ERR_CUDA      = -4,   /* a CUDA runtime call failed */
+    TRQ_ERR_NOMEM     = -5,
+    TRQ_ERR_NO_DEVICE = -6    /* no usable CUDA device: there is no CPU fallback */
+} trq_status;
+
+/* enum struct PrimitiveType  BVH.hh:6-8 */
+enum { TRQ_SPHERE = 0, TRQ_SQUARE = 1, TRQ_CUBE = 2, TRQ_TRIANGLE = 3, TRQ_BVH = 4, TRQ_UNKNOW = 5 };
+
+/* Mirrors struct Primitive (Render.hh:122-130) + element counts. Host pointers; arrays are
+ * copied to the device by trq_scene_create and may be freed by the caller afterwards. */
+typedef struct trq_scene_desc {
+    const void*     sphereList;  uint32_t nSphere;   /* Sphere[nSphere],          272 B each */
+    const void*     squareList;  uint32_t nSquare;   /* Square[nSquare],          272 B each */
+    const void*     cubeList;    uint32_t nCube;     /* Cube[nCube],              240 B each */
+    const void*     triList;     uint32_t nVert;     /* TriangleVertex[nVert],     32 B each */
+    const uint32_t* idxList;     uint32_t nTri;      /* uint32[3*nTri]; leaf pIndex p -> idxList[3p..3p+2] */
+    const void*     bvhList;     uint32_t nNode;     /* BVH[nNode], 64 B each, root at 0 */
+} trq_scene_desc;
+
+/* 32 B. Prefix-compatible with struct Ray (origin@0, direction@16); `tmax` is Scene::hit's
+ * test_t (FLT_MAX for closest-hit of primary/bounce rays, light distance for shadow rays).
+ * `direction` is used as given (Scene::hit never normalises; Ray's ctor already did). */
+typedef struct trq_ray {
+    float    ox, oy, oz, tmax;
+    float    dx, dy, dz;
+    uint32_t flags;              /* reserved, must be 0 */
+} trq_ray;
+
+#define TRQ_HIT_FLAG_HIT   1u
+#define TRQ_HIT_FLAG_FRONT 2u    /* HitRecord::f  (HitRecord.hh:26-29) */
+
+/* 32 B. All-zero on a miss. */
+typedef struct trq_hit {
+    float    t;                  /* HitRecord::t */
+    uint32_t pType;              /* PrimitiveType of the winning leaf */
+    uint32_t pIndex;             /* BVH::pIndex of the winning leaf */
+    uint32_t leafNode;           /* index of the winning leaf in bvhList */
+    float    u, v;               /* triangle: barycentrics u,v (Triangle.hh:61,65); others: HitRecord::uv */
+    uint32_t material;           /* HitRecord::material */
+    uint32_t flags;              /* TRQ_HIT_FLAG_* */
+} trq_hit;
+
+/* 64 B. The HitRecord fields the query writes (for callers that shade). */
+typedef struct trq_hit_record {
+    uint32_t hit;
+    float    t;
+    float    p[3];
+    float    gn[3];
+    float    sn[3];
+    float    uv[2];
+    uint32_t front;
+    uint32_t material;
+    uint32_t pad;
+} trq_hit_record;
+
+typedef struct trq_scene_info_t {
+    uint32_t nNode, nInterior, nLeaf;
+    uint32_t maxDepth;           /* deepest interior level (root = 0); must be <= 31 */
+    uint32_t nTri, nSphere, nSquare, nCube;
+    uint64_t bytesReferenceLayout;   /* device bytes of the six arrays as uploaded */
+    uint64_t bytesPacked;            /* device bytes of the derived traversal layout */
+    int32_t  device;
+    uint32_t pad;
+} trq_scene_info_t;
+
+/* trq_trace / trq_expand_hits flags */
+#define TRQ_TRACE_ANY        0x1u   /* Scene::hit(..., any = true): first accepted hit ends the ray */
+#define TRQ_HOST_PTRS        0x2u   /* rays / hits are HOST pointers: the library stages H2D / D2H
+                                       (chunked, overlapped with tracing) and returns after completion */
+#define TRQ_KERNEL_REFLAYOUT 0x4u   /* run the 1:1 transcription over the reference-layout buffers
+                                       (correctness anchor / naive baseline) instead of the packed kernel */
+
+typedef struct trq_scene trq_scene;
+
+int  trq_version(void);
+const char* trq_last_error_string(void);
+int  trq_device_count(void);
+
+/* Uploads the six arrays to `device`, validates the tree (indices in range, 2N-1 nodes
+ * reachable, depth <= 32) and derives the packed traversal layout on the device. */
+int  trq_scene_create(const trq_scene_desc* desc, int device, trq_scene** out);
+int  trq_scene_destroy(trq_scene* scene);
+int  trq_scene_info(const trq_scene* scene, trq_scene_info_t* info);
+
+/* Scene::hit for n rays. Device pointers unless TRQ_HOST_PTRS; asynchronous on `stream`
+ * (a cudaStream_t, NULL = default stream) for device pointers. Re-entrant across streams. */
+int  trq_trace(trq_scene* scene, const trq_ray* rays, uint64_t n, uint32_t flags,
+               trq_hit* hits, void* stream);
+
+/* Fills HitRecord fields p, gn, sn, uv, f, material for hits produced by trq_trace. */
+int  trq_expand_hits(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n,
+                     uint32_t flags, trq_hit_record* records, void* stream);
+
+/* Number of kernel launches issued by this library in this process (bench evidence). */
+uint64_t trq_launch_count(void);
+
+/* ---- host side: reference scene preparation, restated (BVH.hh:246-314) ------------------- */
+
+/* BVH::buildNode: world AABB of the 8 corners of [box_min, box_max] under the column-major
+ * model matrix; writes one 64-B leaf. model == NULL means identity. */
+int  trq_bvh_build_node(const float box_min[3], const float box_max[3], const float model[16],
+                        int32_t pType, uint32_t pIndex, void* node_out);
+
+/* Per-triangle leaves as AAPLRenderer.mm:575-589 does: box = min/max of the 3 vertices,
+ * identity model, pType = Triangle, pIndex = pIndexBase + i. Writes nTri 64-B nodes. */
+int  trq_bvh_build_nodes_triangles(const void* triList, const uint32_t* idxList, uint32_t nTri,
+                                   uint32_t pIndexBase, void* nodes_out);
+
+/* BVH::buildTree: on entry bvhList[0..nLeaves) are leaves (capacity >= 2*nLeaves-1 nodes);
+ * on return the array holds the reference's final order: root at 0, leaves at 1..nLeaves,
+ * interiors after, parent/left/right = final indices. Sequential variant (deterministic). */
+int  trq_bvh_build_tree(void* bvhList, uint32_t nLeaves, uint32_t* nNodeOut, uint32_t* maxDepthOut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRACER_RQ_H */

@@ -1,0 +1,212 @@
+"""ctypes front-end of the two oracle libraries -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+  Port       oracle/liboracle_rq.so        plain-C restatement, instrumented (oracle_rq.c)
+  Reference  oracle/_ref/libtracer_ref.so  the reference's Render.hh compiled verbatim (ref_scene_hit.cpp)
+
+Both take the same reference-layout arrays as tracer_b200.Primitive.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from tracer_b200 import layout as L
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_PATH = os.path.join(_HERE, "liboracle_rq.so")
+REF_PATH = os.path.join(_HERE, "_ref", "libtracer_ref.so")
+
+counters_dtype = np.dtype([(k, "<u4") for k in
+                           ("n_fp", "n_fc", "n_disp", "n_tri", "n_sph", "n_sq", "n_cube", "n_tie", "n_quirk", "max_level")])
+TOTAL_KEYS = [k for k, _ in counters_dtype.descr]
+
+
+def build(which=("port", "ref")):
+    subprocess.run(["make", "-s", "-C", _HERE] + list(which), check=True)
+
+
+class _Prims(C.Structure):
+    _fields_ = [("sphereList", C.c_void_p), ("squareList", C.c_void_p), ("cubeList", C.c_void_p),
+                ("triList", C.c_void_p), ("idxList", C.c_void_p), ("bvhList", C.c_void_p)]
+
+
+def _prims(p):
+    q = _Prims()
+    for k in ("sphereList", "squareList", "cubeList", "triList", "idxList", "bvhList"):
+        a = getattr(p, k)
+        setattr(q, k, a.ctypes.data if a.size else None)
+    return q
+
+
+def _fp(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Port:
+    """The C restatement (kind "port")."""
+
+    def __init__(self):
+        if not os.path.exists(PORT_PATH):
+            build(("port",))
+        self.lib = C.CDLL(PORT_PATH)
+        self.lib.orq_algorithmic_bytes.restype = C.c_uint64
+
+    def trace(self, prim, rays, any=False, nthreads=1, records=False, counters=False):
+        rays = np.ascontiguousarray(rays)
+        n = rays.size
+        hits = np.zeros(n, dtype=L.hit_dtype)
+        recs = np.zeros(n, dtype=L.record_dtype) if records else None
+        cnts = np.zeros(n, dtype=counters_dtype) if counters else None
+        totals = np.zeros(10, dtype=np.uint64)
+        q = _prims(prim)
+        self.lib.orq_trace(C.byref(q), C.c_void_p(rays.ctypes.data), C.c_uint64(n), C.c_int(1 if any else 0), C.c_int(nthreads),
+                           C.c_void_p(hits.ctypes.data), C.c_void_p(recs.ctypes.data if records else None),
+                           C.c_void_p(cnts.ctypes.data if counters else None), C.c_void_p(totals.ctypes.data))
+        tot = dict(zip(TOTAL_KEYS, (int(x) for x in totals)))
+        tot["bytes"] = int(self.lib.orq_algorithmic_bytes(C.c_void_p(totals.ctypes.data), C.c_uint64(n)))
+        tot["n_rays"] = n
+        return {"hits": hits, "records": recs, "counters": cnts, "totals": tot}
+
+    def aabb_hit_t(self, box8, o, d, rng):
+        box8, o, d, rng = _fp(box8), _fp(o), _fp(d), _fp(rng)
+        t = C.c_float(0)
+        h = self.lib.orq_aabb_hit_t(C.c_void_p(box8.ctypes.data), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data),
+                                    C.c_void_p(rng.ctypes.data), C.byref(t))
+        return bool(h), np.float32(t.value)
+
+    def aabb_hit(self, box8, o, d, rng):
+        box8, o, d, rng = _fp(box8), _fp(o), _fp(d), _fp(rng)
+        return bool(self.lib.orq_aabb_hit(C.c_void_p(box8.ctypes.data), C.c_void_p(o.ctypes.data),
+                                          C.c_void_p(d.ctypes.data), C.c_void_p(rng.ctypes.data)))
+
+    def _leaf(self, fn, obj, o, d, rng, extra=None):
+        o, d = _fp(o), _fp(d)
+        rng = _fp(rng).copy()
+        rec = np.zeros(1, dtype=L.record_dtype)
+        args = [C.c_void_p(obj.ctypes.data)] + ([] if extra is None else [C.c_void_p(extra.ctypes.data)]) + \
+               [C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(rng.ctypes.data), C.c_void_p(rec.ctypes.data)]
+        return fn, args, rng, rec
+
+    def triangle_hit(self, triList, abc, o, d, rng):
+        abc = np.ascontiguousarray(abc, dtype=np.uint32)
+        fn, args, rng, rec = self._leaf(self.lib.orq_triangle_hit, triList, o, d, rng, extra=abc)
+        bary = np.zeros(2, dtype=np.float32)
+        h = fn(*args, C.c_void_p(bary.ctypes.data))
+        return bool(h), rng, rec[0], bary
+
+    def sphere_hit(self, sphere, o, d, rng):
+        fn, args, rng, rec = self._leaf(self.lib.orq_sphere_hit, np.ascontiguousarray(sphere), o, d, rng)
+        return bool(fn(*args)), rng, rec[0]
+
+    def square_hit(self, square, o, d, rng):
+        fn, args, rng, rec = self._leaf(self.lib.orq_square_hit, np.ascontiguousarray(square), o, d, rng)
+        return bool(fn(*args)), rng, rec[0]
+
+    def cube_hit(self, cube, o, d, rng):
+        fn, args, rng, rec = self._leaf(self.lib.orq_cube_hit, np.ascontiguousarray(cube), o, d, rng)
+        return bool(fn(*args)), rng, rec[0]
+
+    def offset_ray(self, p, n):
+        p, n = _fp(p), _fp(n)
+        out = np.zeros(3, dtype=np.float32)
+        self.lib.orq_offset_ray(C.c_void_p(p.ctypes.data), C.c_void_p(n.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
+
+class Reference:
+    """The reference's own headers compiled verbatim (kind "reference"). Only where oracle/_ref was built."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_PATH)
+
+    def __init__(self):
+        if not os.path.exists(REF_PATH):
+            if os.path.isdir("/root/reference/RT_Metal/Metal"):
+                build(("ref",))
+            else:
+                raise FileNotFoundError(REF_PATH)
+        self.lib = C.CDLL(REF_PATH)
+        self.lib.ref_next_float_up.restype = C.c_float
+        self.lib.ref_next_float_up.argtypes = [C.c_float]
+        self.lib.ref_next_float_down.restype = C.c_float
+        self.lib.ref_next_float_down.argtypes = [C.c_float]
+
+    def sizes(self):
+        out = (C.c_uint32 * 32)()
+        self.lib.ref_sizes(out)
+        return list(out)
+
+    def trace(self, prim, rays, any=False, nthreads=1):
+        rays = np.ascontiguousarray(rays)
+        recs = np.zeros(rays.size, dtype=L.record_dtype)
+        q = _prims(prim)
+        self.lib.ref_scene_hit(C.byref(q), C.c_void_p(rays.ctypes.data), C.c_uint64(rays.size), C.c_int(1 if any else 0),
+                               C.c_int(nthreads), C.c_void_p(recs.ctypes.data))
+        return recs
+
+    def trace_lite(self, prim, rays, any=False, nthreads=1):
+        rays = np.ascontiguousarray(rays)
+        hit = np.zeros(rays.size, dtype=np.uint32)
+        t = np.zeros(rays.size, dtype=np.float32)
+        q = _prims(prim)
+        self.lib.ref_scene_hit_lite(C.byref(q), C.c_void_p(rays.ctypes.data), C.c_uint64(rays.size), C.c_int(1 if any else 0),
+                                    C.c_int(nthreads), C.c_void_p(hit.ctypes.data), C.c_void_p(t.ctypes.data))
+        return hit, t
+
+    def aabb_hit_t(self, box8, o, d, rng):
+        box8, o, d, rng = _fp(box8), _fp(o), _fp(d), _fp(rng)
+        t = C.c_float(0)
+        h = self.lib.ref_aabb_hit_t(C.c_void_p(box8.ctypes.data), C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data),
+                                    C.c_void_p(rng.ctypes.data), C.byref(t))
+        return bool(h), np.float32(t.value)
+
+    def aabb_hit(self, box8, o, d, rng):
+        box8, o, d, rng = _fp(box8), _fp(o), _fp(d), _fp(rng)
+        return bool(self.lib.ref_aabb_hit(C.c_void_p(box8.ctypes.data), C.c_void_p(o.ctypes.data),
+                                          C.c_void_p(d.ctypes.data), C.c_void_p(rng.ctypes.data)))
+
+    def _leaf(self, fn, obj, o, d, rng, extra=None):
+        o, d = _fp(o), _fp(d)
+        rng = _fp(rng).copy()
+        rec = np.zeros(1, dtype=L.record_dtype)
+        args = [C.c_void_p(obj.ctypes.data)] + ([] if extra is None else [C.c_void_p(extra.ctypes.data)]) + \
+               [C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(rng.ctypes.data), C.c_void_p(rec.ctypes.data)]
+        return bool(fn(*args)), rng, rec[0]
+
+    def triangle_hit(self, triList, abc, o, d, rng):
+        return self._leaf(self.lib.ref_triangle_hit, triList, o, d, rng, extra=np.ascontiguousarray(abc, dtype=np.uint32))
+
+    def sphere_hit(self, sphere, o, d, rng):
+        return self._leaf(self.lib.ref_sphere_hit, np.ascontiguousarray(sphere), o, d, rng)
+
+    def square_hit(self, square, o, d, rng):
+        return self._leaf(self.lib.ref_square_hit, np.ascontiguousarray(square), o, d, rng)
+
+    def cube_hit(self, cube, o, d, rng):
+        return self._leaf(self.lib.ref_cube_hit, np.ascontiguousarray(cube), o, d, rng)
+
+    def offset_ray(self, p, n):
+        p, n = _fp(p), _fp(n)
+        out = np.zeros(3, dtype=np.float32)
+        self.lib.ref_offset_ray(C.c_void_p(p.ctypes.data), C.c_void_p(n.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
+    def ray_ctor(self, o, d):
+        o, d = _fp(o), _fp(d)
+        oo, dd = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        self.lib.ref_ray_ctor(C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(oo.ctypes.data), C.c_void_p(dd.ctypes.data))
+        return oo, dd
+
+    def coordinate_system(self, a):
+        a = _fp(a)
+        b, c = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        self.lib.ref_coordinate_system(C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), C.c_void_p(c.ctypes.data))
+        return b, c
+
+    def cosine_sample_hemisphere(self, u):
+        u = _fp(u)
+        out = np.zeros(3, dtype=np.float32)
+        self.lib.ref_cosine_sample_hemisphere(C.c_void_p(u.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out

@@ -1,0 +1,66 @@
+// tracer_b200/csrc/kernels/scene_dev.cuh -- device-side view of a scene + packed layout encoding.
+//
+// Data layout in HBM:
+//   reference arrays, byte-for-byte as uploaded   spheres / squares / cubes / verts / idx / bvh
+//   packed interior nodes  64 B = 4 x float4, 64-B aligned, one per interior BVH node, in
+//     depth-first order (root = 0):
+//       q0 = { left.mini.xyz , bits(leftRef)  }    q1 = { left.maxi.xyz , bits(rightRef) }
+//       q2 = { right.mini.xyz, 0 }                 q3 = { right.maxi.xyz, 0 }
+//     Both child boxes live in the parent: one 64-B fetch per from-parent step instead of the
+//     reference's 12 B of links + two scattered 32-B boxes + 8 B of child type (Render.hh:151-160,211-213).
+//   packed triangles 48 B = 3 x float4 per triangle LEAF, in depth-first leaf order:
+//       t0 = { v0.xyz, bits(leafNode) }  t1 = { v1 - v0, 0 }  t2 = { v2 - v0, 0 }
+//     (the two edge subtractions are the first operations of Triangle::hit_test, Triangle.hh:43-44)
+//   packed spheres 32 B = 2 x float4 per sphere LEAF:
+//       s0 = { center.xyz, radius }      s1 = { bits(leafNode), 0, 0, 0 }
+//
+// Child reference (32 bit): kind in bits 31..29, index in bits 28..0.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../host/layout.h"
+
+namespace trq {
+
+enum : uint32_t {
+    REF_INTERIOR = 0u,   // index = packed interior node
+    REF_TRI      = 1u,   // index = packed triangle slot
+    REF_SPHERE   = 2u,   // index = packed sphere slot
+    REF_SQUARE   = 3u,   // index = leaf node in bvhList (reads the reference-layout Square)
+    REF_CUBE     = 4u,   // index = leaf node in bvhList (reads the reference-layout Cube)
+    REF_NOP      = 6u,   // leaf whose pType dispatches to `default: break` (Render.hh:241)
+    REF_DONE     = 7u    // traversal finished (never stored in a node)
+};
+#define TRQ_REF_KIND(r)  ((r) >> 29)
+#define TRQ_REF_INDEX(r) ((r) & 0x1fffffffu)
+#define TRQ_MAKE_REF(kind, index) (((uint32_t)(kind) << 29) | (uint32_t)(index))
+#define TRQ_REF_DONE_WORD 0xffffffffu
+
+struct SceneDev {
+    const RefSphere* spheres;
+    const RefSquare* squares;
+    const RefCube*   cubes;
+    const RefVertex* verts;
+    const uint32_t*  idx;
+    const RefBVH*    bvh;
+    const float4*    nodes;     // 4 per interior node
+    const float4*    tris;      // 3 per triangle leaf
+    const float4*    sph;       // 2 per sphere leaf
+    uint32_t         rootRef;
+    float            rootMin[3], rootMax[3];
+    uint32_t         nNode;
+};
+
+// Compact per-ray result written by the trace kernels, resolved into trq_hit by resolve_hits.
+// Same 32-B footprint as trq_hit so it is resolved in place.
+struct CompactHit {
+    float    t;
+    uint32_t leafNode;   // bvhList index of the winning leaf
+    float    u, v;       // triangle barycentrics / cube uv captured at hit time
+    uint32_t aux;        // cube: front | material << 1
+    uint32_t hit;        // 0 / 1
+    uint32_t pad0, pad1;
+};
+
+}  // namespace trq

@@ -1,0 +1,345 @@
+// tracer_b200/csrc/kernels/trace_kernels.cuh -- the ray-query kernels (sm_100a).
+//
+//   trace_reflayout_kernel  1:1 transcription of Scene::hit (Render.hh:135-252) over the reference-
+//                           layout buffers: parent links + 32-bit trail, one thread per ray.
+//                           Correctness anchor and naive baseline.
+//   trace_packed_kernel     the product kernel: persistent warps pull rays from a global queue with
+//                           one warp-aggregated atomic per refill, traverse the packed 64-B fused
+//                           nodes with 256-bit loads, and keep the far children of "both hit" nodes
+//                           on a per-lane shared-memory stack. The stack replaces the reference's
+//                           from-child steps (re-reading parent links, Render.hh:189-209); the visit
+//                           ORDER per ray is exactly the reference's: near child first by hit_t's t,
+//                           ties to the right child, the far child decided at first arrival and never
+//                           re-tested, including the "select the missed child" quirk of Render.hh:174.
+//   resolve_hits_kernel     compact result -> trq_hit (pType, pIndex, front, material, sphere uv)
+//   expand_hits_kernel      trq_hit -> HitRecord fields (p, gn, sn, uv, f, material)
+#pragma once
+#include <cfloat>
+
+#include "../../../include/tracer_rq.h"
+#include "intersect.cuh"
+#include "scene_dev.cuh"
+
+namespace trq {
+
+// ---------------------------------------------------------------------------------------------
+// loads
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// 256-bit read-only load (LDG.E.256 on sm_100): two float4 from a 32-byte aligned address.
+__device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
+__device__ __forceinline__ void store_compact(trq_hit* hits, uint64_t i, bool hit, float t, uint32_t leaf,
+                                              float u, float v, uint32_t aux) {
+    float4 a, b;
+    a.x = hit ? t : 0.0f;
+    a.y = __uint_as_float(hit ? leaf : 0u);
+    a.z = hit ? u : 0.0f;
+    a.w = hit ? v : 0.0f;
+    b.x = __uint_as_float(hit ? aux : 0u);
+    b.y = __uint_as_float(hit ? 1u : 0u);
+    b.z = 0.0f; b.w = 0.0f;
+    float4* out = reinterpret_cast<float4*>(hits + i);
+    out[0] = a; out[1] = b;
+}
+
+// Leaf tests that read reference-layout structs (rare leaf types). Returns true on accept.
+__device__ __forceinline__ bool leaf_square_cube(const SceneDev& S, uint32_t kind, uint32_t leafNode, const RayCtx& ray,
+                                                 float range_y, float& t, float& u, float& v, uint32_t& aux) {
+    const uint32_t pIndex = S.bvh[leafNode].pIndex;
+    if (kind == REF_SQUARE) {
+        return square_hit(&S.squares[pIndex], ray, FLT_MIN, range_y, t, nullptr);
+    }
+    Surface s;
+    if (!cube_hit(&S.cubes[pIndex], ray, FLT_MIN, range_y, t, &s)) return false;
+    u = s.uvx; v = s.uvy; aux = s.front | (s.material << 1);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// v0: reference layout, reference control flow.
+template <bool ANY>
+__global__ void __launch_bounds__(128)
+trace_reflayout_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* __restrict__ hits, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
+    const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+    const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+    const float test_t = r0.w;
+    const RefBVH* __restrict__ N = S.bvh;
+
+    uint32_t the_index = 0, tested_index = 0xffffffffu;                   // Render.hh:137-138
+    uint32_t stack_mark = 0, stack_level = 0;                             // :140-141
+    float range_y = test_t;                                               // :143  range_t = (FLT_MIN, test_t)
+    uint32_t best = 0xffffffffu, aux = 0; float bu = 0.0f, bv = 0.0f;
+    bool done_any = false;
+
+    if (box_hit(ld3(N[0].bBOX.mini), ld3(N[0].bBOX.maxi), ray, FLT_MIN, range_y)) {   // :145
+        do {
+            uint32_t sel;
+            const uint4 links = *reinterpret_cast<const uint4*>(&N[the_index]);       // parent,left,right,axis :151-153
+            const uint32_t p = links.x, l = links.y, r = links.z;
+            if (tested_index != l && tested_index != r) {                 // :155
+                float tl = range_y, tr = range_y;                         // :157
+                const bool lt = box_hit_t(ld3(N[l].bBOX.mini), ld3(N[l].bBOX.maxi), ray, FLT_MIN, range_y, tl);   // :159
+                const bool rt = box_hit_t(ld3(N[r].bBOX.mini), ld3(N[r].bBOX.maxi), ray, FLT_MIN, range_y, tr);   // :160
+                if (!lt && !rt) { tested_index = the_index; the_index = p; stack_level -= 1; continue; }          // :162-169
+                if (lt && rt) stack_mark |= 1u << (stack_level & 31u);    // :171-172
+                sel = (tl < tr) ? l : r;                                  // :174
+            } else {
+                const uint32_t need = (stack_mark >> (stack_level & 31u)) & 1u;       // :191
+                stack_mark &= ~(1u << (stack_level & 31u));               // :193
+                if (need == 0) { tested_index = the_index; the_index = p; stack_level -= 1; continue; }           // :195-202
+                sel = (tested_index == l) ? r : l;                        // :204-208
+            }
+            const int32_t pType = N[sel].pType;                           // :211-213
+            const uint32_t pIndex = N[sel].pIndex;
+            bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t a = 0;
+            if (pType == TRQ_BVH) { the_index = sel; stack_level += 1; continue; }    // :215-220
+            if (pType == TRQ_TRIANGLE) {                                  // :230-240
+                const f3 v0 = ld3(S.verts[S.idx[3 * pIndex]].v);
+                const f3 v1 = ld3(S.verts[S.idx[3 * pIndex + 1]].v);
+                const f3 v2 = ld3(S.verts[S.idx[3 * pIndex + 2]].v);
+                h = tri_hit(v0, sub3(v1, v0), sub3(v2, v0), ray, FLT_MIN, range_y, t, u, v);
+            } else if (pType == TRQ_SPHERE) {                             // :221-223
+                h = sphere_hit(ld3(S.spheres[pIndex].center), S.spheres[pIndex].radius, ray, FLT_MIN, range_y, t);
+            } else if (pType == TRQ_SQUARE || pType == TRQ_CUBE) {        // :224-229
+                h = leaf_square_cube(S, pType == TRQ_SQUARE ? REF_SQUARE : REF_CUBE, sel, ray, range_y, t, u, v, a);
+            }
+            if (h) { range_y = t; best = sel; bu = u; bv = v; aux = a; }
+            if (ANY && range_y < test_t) { done_any = true; break; }      // :244
+            tested_index = sel;                                           // :246
+        } while (tested_index != 0);                                      // :248
+    }
+    const bool hit = done_any || (range_y < test_t);                      // :251
+    store_compact(hits, i, hit && best != 0xffffffffu, range_y, best, bu, bv, aux);
+}
+
+// ---------------------------------------------------------------------------------------------
+// v1: packed layout, persistent warps, shared-memory far-child stack.
+#ifndef TRQ_BLOCK
+#define TRQ_BLOCK 256
+#endif
+
+struct TraceParams {
+    const trq_ray* rays;
+    trq_hit*       hits;
+    uint64_t       n;
+    unsigned long long* counter;   // global ray queue head
+    uint32_t       stackDepth;     // entries per lane
+    uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
+};
+
+template <bool ANY>
+__global__ void __launch_bounds__(TRQ_BLOCK)
+trace_packed_kernel(const SceneDev S, const TraceParams P) {
+    extern __shared__ uint32_t smem_stack[];                 // [stackDepth][TRQ_BLOCK]: lane-major => conflict-free
+    uint32_t* const stk = smem_stack + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
+    const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
+
+    bool active = false, exhausted = false;
+    uint64_t rayIdx = 0;
+    RayCtx ray; ray.o = ray.d = ray.inv = make_f3(0.f, 0.f, 0.f);
+    float test_t = 0.0f, range_y = 0.0f, bu = 0.0f, bv = 0.0f;
+    uint32_t cur = TRQ_REF_DONE_WORD, sp = 0, best = 0xffffffffu, aux = 0;
+
+    for (;;) {
+        // ---- refill idle lanes from the global queue: one atomic per warp ----
+        const unsigned idleMask = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idleMask == 0xffffffffu || __popc(idleMask) >= (int)P.refillMin)) {
+            const int want = __popc(idleMask);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)want);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base + (unsigned long long)want >= P.n) exhausted = true;
+            if (!active) {
+                const uint64_t idx = base + (uint64_t)__popc(idleMask & ((1u << lane) - 1u));
+                if (idx < P.n) {
+                    rayIdx = idx;
+                    const float4 r0 = ldg4(reinterpret_cast<const float4*>(P.rays + idx));
+                    const float4 r1 = ldg4(reinterpret_cast<const float4*>(P.rays + idx) + 1);
+                    ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                    test_t = r0.w; range_y = r0.w;                        // Render.hh:143
+                    best = 0xffffffffu; bu = bv = 0.0f; aux = 0; sp = 0;
+                    if (box_hit(rootMin, rootMax, ray, FLT_MIN, range_y)) {            // :145
+                        cur = S.rootRef; active = true;
+                    } else {
+                        store_compact(P.hits, idx, false, 0.0f, 0u, 0.0f, 0.0f, 0u);
+                    }
+                }
+            }
+        }
+        const unsigned actMask = __ballot_sync(0xffffffffu, active);
+        if (actMask == 0u) { if (exhausted) break; else continue; }
+
+        // ---- traverse until enough lanes have retired to make a refill worthwhile ----
+        const int keepGoing = exhausted ? 0 : (32 - (int)P.refillMin);
+        do {
+            if (active) {
+                const uint32_t kind = TRQ_REF_KIND(cur);
+                if (kind == REF_INTERIOR) {
+                    const float4* np = S.nodes + (size_t)TRQ_REF_INDEX(cur) * 4u;
+                    float4 q0, q1, q2, q3;
+                    ldg8(np, q0, q1);
+                    ldg8(np + 2, q2, q3);
+                    float tl = range_y, tr = range_y;                     // :157
+                    const bool lt = box_hit_t(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ray, FLT_MIN, range_y, tl);
+                    const bool rt = box_hit_t(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ray, FLT_MIN, range_y, tr);
+                    const uint32_t lref = __float_as_uint(q0.w), rref = __float_as_uint(q1.w);
+                    if (!lt && !rt) {                                     // :162-169  pop
+                        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * TRQ_BLOCK]; }
+                    } else {
+                        const bool selLeft = tl < tr;                     // :174 (ties -> right, quirk included)
+                        if (lt && rt) { stk[sp * TRQ_BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
+                        cur = selLeft ? lref : rref;
+                    }
+                } else {
+                    bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t leaf = 0, a = 0;
+                    if (kind == REF_TRI) {
+                        const float4* tp = S.tris + (size_t)TRQ_REF_INDEX(cur) * 3u;
+                        const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
+                        leaf = __float_as_uint(t0.w);
+                        h = tri_hit(make_f3(t0.x, t0.y, t0.z), make_f3(t1.x, t1.y, t1.z), make_f3(t2.x, t2.y, t2.z),
+                                    ray, FLT_MIN, range_y, t, u, v);
+                    } else if (kind == REF_SPHERE) {
+                        const float4* spp = S.sph + (size_t)TRQ_REF_INDEX(cur) * 2u;
+                        const float4 s0 = ldg4(spp), s1 = ldg4(spp + 1);
+                        leaf = __float_as_uint(s1.x);
+                        h = sphere_hit(make_f3(s0.x, s0.y, s0.z), s0.w, ray, FLT_MIN, range_y, t);
+                    } else if (kind == REF_SQUARE || kind == REF_CUBE) {
+                        leaf = TRQ_REF_INDEX(cur);
+                        h = leaf_square_cube(S, kind, leaf, ray, range_y, t, u, v, a);
+                    }
+                    if (h) { range_y = t; best = leaf; bu = u; bv = v; aux = a; }
+                    if (ANY && range_y < test_t) cur = TRQ_REF_DONE_WORD; // :244
+                    else if (sp == 0) cur = TRQ_REF_DONE_WORD;
+                    else { --sp; cur = stk[sp * TRQ_BLOCK]; }
+                }
+                if (cur == TRQ_REF_DONE_WORD) {
+                    const bool hit = (range_y < test_t) && best != 0xffffffffu;       // :251
+                    store_compact(P.hits, rayIdx, hit, range_y, best, bu, bv, aux);
+                    active = false;
+                }
+            }
+        } while (__popc(__ballot_sync(0xffffffffu, active)) > keepGoing);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compact -> trq_hit, in place. One thread per ray, fully coalesced.
+__global__ void __launch_bounds__(256)
+resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4* io = reinterpret_cast<float4*>(hits + i);
+    const float4 a = io[0], b = io[1];
+    trq_hit out;
+    out.t = 0.0f; out.pType = 0; out.pIndex = 0; out.leafNode = 0; out.u = 0.0f; out.v = 0.0f; out.material = 0; out.flags = 0;
+    if (__float_as_uint(b.y) != 0u) {
+        const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
+        const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+        const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+        const uint32_t leaf = __float_as_uint(a.y);
+        const int32_t pType = S.bvh[leaf].pType;
+        const uint32_t pIndex = S.bvh[leaf].pIndex;
+        out.t = a.x; out.pType = (uint32_t)pType; out.pIndex = pIndex; out.leafNode = leaf;
+        Surface s; s.front = 0; s.material = 0; s.uvx = s.uvy = 0.0f;
+        if (pType == TRQ_TRIANGLE) {
+            tri_surface(S.verts, S.idx, pIndex, a.z, a.w, ray, s);
+            out.u = a.z; out.v = a.w;
+        } else if (pType == TRQ_SPHERE) {
+            sphere_surface(&S.spheres[pIndex], a.x, ray, s);
+            out.u = s.uvx; out.v = s.uvy;
+        } else if (pType == TRQ_SQUARE) {
+            float t;
+            square_hit(&S.squares[pIndex], ray, a.x, a.x, t, &s);          // same t -> same a, b, uv
+            out.u = s.uvx; out.v = s.uvy;
+        } else if (pType == TRQ_CUBE) {
+            const uint32_t aux = __float_as_uint(b.x);
+            s.front = aux & 1u; s.material = aux >> 1;
+            out.u = a.z; out.v = a.w;
+        }
+        out.material = s.material;
+        out.flags = TRQ_HIT_FLAG_HIT | (s.front ? TRQ_HIT_FLAG_FRONT : 0u);
+    }
+    float4 o0, o1;
+    o0.x = out.t; o0.y = __uint_as_float(out.pType); o0.z = __uint_as_float(out.pIndex); o0.w = __uint_as_float(out.leafNode);
+    o1.x = out.u; o1.y = out.v; o1.z = __uint_as_float(out.material); o1.w = __uint_as_float(out.flags);
+    io[0] = o0; io[1] = o1;
+}
+
+// trq_hit -> HitRecord fields.
+__global__ void __launch_bounds__(256)
+expand_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, const trq_hit* __restrict__ hits,
+                   trq_hit_record* __restrict__ recs, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const trq_hit h = hits[i];
+    trq_hit_record out;
+    out.hit = 0; out.t = 0.0f; out.front = 0; out.material = 0; out.pad = 0;
+    out.p[0] = out.p[1] = out.p[2] = 0.0f; out.gn[0] = out.gn[1] = out.gn[2] = 0.0f;
+    out.sn[0] = out.sn[1] = out.sn[2] = 0.0f; out.uv[0] = out.uv[1] = 0.0f;
+    if (h.flags & TRQ_HIT_FLAG_HIT) {
+        const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
+        const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+        const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+        Surface s; s.p = s.gn = s.sn = make_f3(0.f, 0.f, 0.f); s.uvx = s.uvy = 0.0f; s.front = 0; s.material = 0;
+        float t;
+        if (h.pType == TRQ_TRIANGLE)     tri_surface(S.verts, S.idx, h.pIndex, h.u, h.v, ray, s);
+        else if (h.pType == TRQ_SPHERE)  sphere_surface(&S.spheres[h.pIndex], h.t, ray, s);
+        else if (h.pType == TRQ_SQUARE)  square_hit(&S.squares[h.pIndex], ray, h.t, h.t, t, &s);
+        else if (h.pType == TRQ_CUBE)    cube_hit(&S.cubes[h.pIndex], ray, FLT_MIN, FLT_MAX, t, &s);
+        out.hit = 1; out.t = h.t;
+        out.p[0] = s.p.x; out.p[1] = s.p.y; out.p[2] = s.p.z;
+        out.gn[0] = s.gn.x; out.gn[1] = s.gn.y; out.gn[2] = s.gn.z;
+        out.sn[0] = s.sn.x; out.sn[1] = s.sn.y; out.sn[2] = s.sn.z;
+        out.uv[0] = s.uvx; out.uv[1] = s.uvy;
+        out.front = s.front; out.material = s.material;
+    }
+    recs[i] = out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// derive the packed layout from the reference-layout buffers (one thread per BVH node)
+__global__ void __launch_bounds__(256)
+pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ ref, uint32_t nNode,
+                  const RefVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
+                  const RefSphere* __restrict__ spheres,
+                  float4* __restrict__ nodes, float4* __restrict__ tris, float4* __restrict__ sph) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nNode) return;
+    const uint32_t my = ref[i];
+    const uint32_t kind = TRQ_REF_KIND(my), slot = TRQ_REF_INDEX(my);
+    if (my == TRQ_REF_DONE_WORD) return;                      // unreachable node
+    if (kind == REF_INTERIOR) {
+        const uint32_t l = bvh[i].left, r = bvh[i].right;
+        const RefAABB lb = bvh[l].bBOX, rb = bvh[r].bBOX;
+        float4* out = nodes + (size_t)slot * 4u;
+        out[0] = make_float4(lb.mini[0], lb.mini[1], lb.mini[2], __uint_as_float(ref[l]));
+        out[1] = make_float4(lb.maxi[0], lb.maxi[1], lb.maxi[2], __uint_as_float(ref[r]));
+        out[2] = make_float4(rb.mini[0], rb.mini[1], rb.mini[2], 0.0f);
+        out[3] = make_float4(rb.maxi[0], rb.maxi[1], rb.maxi[2], 0.0f);
+    } else if (kind == REF_TRI) {
+        const uint32_t p = bvh[i].pIndex;
+        const f3 v0 = ld3(verts[idx[3 * p]].v), v1 = ld3(verts[idx[3 * p + 1]].v), v2 = ld3(verts[idx[3 * p + 2]].v);
+        const f3 e1 = sub3(v1, v0), e2 = sub3(v2, v0);       // Triangle.hh:43-44
+        float4* out = tris + (size_t)slot * 3u;
+        out[0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(i));
+        out[1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
+        out[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+    } else if (kind == REF_SPHERE) {
+        const RefSphere* s = &spheres[bvh[i].pIndex];
+        float4* out = sph + (size_t)slot * 2u;
+        out[0] = make_float4(s->center[0], s->center[1], s->center[2], s->radius);
+        out[1] = make_float4(__uint_as_float(i), 0.0f, 0.0f, 0.0f);
+    }
+}
+
+}  // namespace trq

@@ -1,0 +1,417 @@
+// tracer_b200/csrc/trq_api.cu -- implementation of the C-ABI in include/tracer_rq.h.
+//
+// Host side of the drop-in boundary: it takes the six reference-layout arrays exactly as
+// AAPLRenderer.mm:614-624,712-720 hands them to Metal (struct Primitive, Render.hh:122-130),
+// uploads them, derives the packed traversal layout ON THE DEVICE (pack_scene_kernel), and runs
+// batches of Scene::hit (Render.hh:135-252) as CUDA kernels. No CPU fallback exists: without a
+// device every compute entry point returns TRQ_ERR_NO_DEVICE.
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/tracer_rq.h"
+#include "host/error.h"
+#include "host/layout.h"
+#include "kernels/trace_kernels.cuh"
+
+using namespace trq;
+
+namespace {
+
+std::atomic<uint64_t> g_launches{0};
+
+#define TRQ_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return trq::fail(TRQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+constexpr int kCounterRing = 256;
+constexpr int kStageBufs = 3;
+
+}  // namespace
+
+struct trq_scene {
+    int device = 0;
+    int numSMs = 0;
+    trq_scene_info_t info{};
+    // reference-layout device copies (struct Primitive)
+    RefSphere* d_spheres = nullptr;
+    RefSquare* d_squares = nullptr;
+    RefCube*   d_cubes = nullptr;
+    RefVertex* d_verts = nullptr;
+    uint32_t*  d_idx = nullptr;
+    RefBVH*    d_bvh = nullptr;
+    // packed layout
+    float4* d_nodes = nullptr;
+    float4* d_tris = nullptr;
+    float4* d_sph = nullptr;
+    SceneDev dev{};
+    uint32_t stackDepth = 1;
+    // ray-queue heads
+    unsigned long long* d_counters = nullptr;
+    std::atomic<uint32_t> counterNext{0};
+    // staging for TRQ_HOST_PTRS
+    std::mutex stageMutex;
+    uint64_t stageCap = 0;
+    trq_ray* d_stageRays[kStageBufs] = {nullptr, nullptr, nullptr};
+    trq_hit* d_stageHits[kStageBufs] = {nullptr, nullptr, nullptr};
+    cudaStream_t sH2D = nullptr, sCompute = nullptr, sD2H = nullptr;
+    cudaEvent_t evH2D[kStageBufs] = {}, evCompute[kStageBufs] = {}, evD2H[kStageBufs] = {};
+    bool stageReady = false;
+};
+
+namespace {
+
+void free_scene(trq_scene* s) {
+    if (!s) return;
+    cudaFree(s->d_spheres); cudaFree(s->d_squares); cudaFree(s->d_cubes);
+    cudaFree(s->d_verts); cudaFree(s->d_idx); cudaFree(s->d_bvh);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph);
+    cudaFree(s->d_counters);
+    for (int b = 0; b < kStageBufs; ++b) {
+        cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
+        if (s->evH2D[b]) cudaEventDestroy(s->evH2D[b]);
+        if (s->evCompute[b]) cudaEventDestroy(s->evCompute[b]);
+        if (s->evD2H[b]) cudaEventDestroy(s->evD2H[b]);
+    }
+    if (s->sH2D) cudaStreamDestroy(s->sH2D);
+    if (s->sCompute) cudaStreamDestroy(s->sCompute);
+    if (s->sD2H) cudaStreamDestroy(s->sD2H);
+    delete s;
+}
+
+template <typename T>
+int upload(T** dst, const void* src, size_t count) {
+    *dst = nullptr;
+    if (count == 0) return TRQ_OK;
+    TRQ_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    TRQ_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return TRQ_OK;
+}
+
+// Walk the tree once on the host: validate the layout contract and assign every reachable node its
+// packed reference (interior nodes and leaves numbered in depth-first order, left child first).
+int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_info_t& info) {
+    const RefBVH* N = (const RefBVH*)d->bvhList;
+    const uint32_t n = d->nNode;
+    ref.assign(n, TRQ_REF_DONE_WORD);
+    uint32_t nInterior = 0, nTriLeaf = 0, nSphLeaf = 0, nLeaf = 0, maxDepth = 0;
+    struct Item { uint32_t node, depth; };
+    std::vector<Item> stack;
+    stack.push_back({0u, 0u});
+    while (!stack.empty()) {
+        const Item it = stack.back(); stack.pop_back();
+        const uint32_t i = it.node;
+        if (i >= n) return trq::fail(TRQ_ERR_LAYOUT, "bvhList: child index %u out of range (nNode %u)", i, n);
+        if (ref[i] != TRQ_REF_DONE_WORD) return trq::fail(TRQ_ERR_LAYOUT, "bvhList: node %u reachable twice (not a tree)", i);
+        const RefBVH& b = N[i];
+        if (b.pType == TRQ_BVH) {
+            if (it.depth > 31) return trq::fail(TRQ_ERR_DEPTH, "bvhList: interior depth %u exceeds the 32-bit trail (Render.hh:140)", it.depth);
+            if (b.left == 0 || b.right == 0 || b.left == b.right)
+                return trq::fail(TRQ_ERR_LAYOUT, "bvhList: interior node %u has invalid children (%u, %u)", i, b.left, b.right);
+            if (nInterior >= 0x1fffffffu) return trq::fail(TRQ_ERR_LAYOUT, "bvhList: too many interior nodes");
+            ref[i] = TRQ_MAKE_REF(REF_INTERIOR, nInterior++);
+            maxDepth = it.depth > maxDepth ? it.depth : maxDepth;
+            stack.push_back({b.right, it.depth + 1});     // left is popped (numbered) first
+            stack.push_back({b.left, it.depth + 1});
+        } else {
+            ++nLeaf;
+            switch (b.pType) {
+                case TRQ_TRIANGLE:
+                    if (b.pIndex >= d->nTri) return trq::fail(TRQ_ERR_LAYOUT, "leaf %u: triangle pIndex %u >= nTri %u", i, b.pIndex, d->nTri);
+                    for (int k = 0; k < 3; ++k)
+                        if (d->idxList[3 * (size_t)b.pIndex + k] >= d->nVert)
+                            return trq::fail(TRQ_ERR_LAYOUT, "triangle %u: vertex index out of range", b.pIndex);
+                    ref[i] = TRQ_MAKE_REF(REF_TRI, nTriLeaf++);
+                    break;
+                case TRQ_SPHERE:
+                    if (b.pIndex >= d->nSphere) return trq::fail(TRQ_ERR_LAYOUT, "leaf %u: sphere pIndex %u >= nSphere %u", i, b.pIndex, d->nSphere);
+                    ref[i] = TRQ_MAKE_REF(REF_SPHERE, nSphLeaf++);
+                    break;
+                case TRQ_SQUARE:
+                    if (b.pIndex >= d->nSquare) return trq::fail(TRQ_ERR_LAYOUT, "leaf %u: square pIndex %u >= nSquare %u", i, b.pIndex, d->nSquare);
+                    ref[i] = TRQ_MAKE_REF(REF_SQUARE, i);
+                    break;
+                case TRQ_CUBE:
+                    if (b.pIndex >= d->nCube) return trq::fail(TRQ_ERR_LAYOUT, "leaf %u: cube pIndex %u >= nCube %u", i, b.pIndex, d->nCube);
+                    ref[i] = TRQ_MAKE_REF(REF_CUBE, i);
+                    break;
+                default:
+                    ref[i] = TRQ_MAKE_REF(REF_NOP, i);        // Render.hh:241 `default: break`
+                    break;
+            }
+        }
+    }
+    info.nNode = n; info.nInterior = nInterior; info.nLeaf = nLeaf; info.maxDepth = maxDepth;
+    info.nTri = nTriLeaf; info.nSphere = nSphLeaf;
+    info.nSquare = d->nSquare; info.nCube = d->nCube;
+    return TRQ_OK;
+}
+
+int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, trq_hit* d_hits, cudaStream_t st) {
+    if (n == 0) return TRQ_OK;
+    const bool any = (flags & TRQ_TRACE_ANY) != 0;
+    if (flags & TRQ_KERNEL_REFLAYOUT) {
+        const unsigned block = 128;
+        const uint64_t grid = (n + block - 1) / block;
+        if (grid > 0x7fffffffull) return trq::fail(TRQ_ERR_INVALID, "trq_trace: batch too large");
+        if (any) trace_reflayout_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
+        else     trace_reflayout_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
+        g_launches++;
+    } else {
+        static const uint32_t refillMin = [] {
+            const char* e = getenv("TRQ_REFILL_MIN");
+            int v = e ? atoi(e) : 8;
+            return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
+        }();
+        static const int blocksPerSMOverride = [] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
+        const size_t smem = (size_t)s->stackDepth * TRQ_BLOCK * sizeof(uint32_t);
+        int perSM = 0;
+        if (any) TRQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, trace_packed_kernel<true>, TRQ_BLOCK, smem));
+        else     TRQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, trace_packed_kernel<false>, TRQ_BLOCK, smem));
+        if (perSM < 1) return trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", smem);
+        if (blocksPerSMOverride > 0 && blocksPerSMOverride < perSM) perSM = blocksPerSMOverride;
+        uint64_t grid = (uint64_t)perSM * (uint64_t)s->numSMs;             // persistent: a multiple of the SM count
+        const uint64_t need = (n + TRQ_BLOCK - 1) / TRQ_BLOCK;
+        if (grid > need) grid = need;
+        unsigned long long* counter = s->d_counters + (s->counterNext.fetch_add(1) % kCounterRing);
+        TRQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        TraceParams P;
+        P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
+        P.stackDepth = s->stackDepth; P.refillMin = refillMin;
+        if (any) trace_packed_kernel<true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
+        else     trace_packed_kernel<false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
+        g_launches++;
+    }
+    {
+        const unsigned block = 256;
+        const uint64_t grid = (n + block - 1) / block;
+        resolve_hits_kernel<<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
+        g_launches++;
+    }
+    TRQ_CUDA(cudaGetLastError());
+    return TRQ_OK;
+}
+
+int ensure_staging(trq_scene* s, uint64_t chunk) {
+    if (!s->stageReady) {
+        TRQ_CUDA(cudaStreamCreateWithFlags(&s->sH2D, cudaStreamNonBlocking));
+        TRQ_CUDA(cudaStreamCreateWithFlags(&s->sCompute, cudaStreamNonBlocking));
+        TRQ_CUDA(cudaStreamCreateWithFlags(&s->sD2H, cudaStreamNonBlocking));
+        for (int b = 0; b < kStageBufs; ++b) {
+            TRQ_CUDA(cudaEventCreateWithFlags(&s->evH2D[b], cudaEventDisableTiming));
+            TRQ_CUDA(cudaEventCreateWithFlags(&s->evCompute[b], cudaEventDisableTiming));
+            TRQ_CUDA(cudaEventCreateWithFlags(&s->evD2H[b], cudaEventDisableTiming));
+        }
+        s->stageReady = true;
+    }
+    if (chunk > s->stageCap) {
+        for (int b = 0; b < kStageBufs; ++b) {
+            cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
+            s->d_stageRays[b] = nullptr; s->d_stageHits[b] = nullptr;
+        }
+        s->stageCap = 0;
+        for (int b = 0; b < kStageBufs; ++b) {
+            TRQ_CUDA(cudaMalloc((void**)&s->d_stageRays[b], chunk * sizeof(trq_ray)));
+            TRQ_CUDA(cudaMalloc((void**)&s->d_stageHits[b], chunk * sizeof(trq_hit)));
+        }
+        s->stageCap = chunk;
+    }
+    return TRQ_OK;
+}
+
+// Host-pointer path: H2D of rays, trace, D2H of hits, pipelined over chunks on three streams so
+// that PCIe in both directions overlaps the kernels.
+int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits) {
+    static const uint64_t chunkRays = [] {
+        const char* e = getenv("TRQ_CHUNK_RAYS");
+        long long v = e ? atoll(e) : (2ll << 20);
+        return (uint64_t)(v < 1024 ? 1024 : v);
+    }();
+    std::lock_guard<std::mutex> lock(s->stageMutex);
+    const uint64_t chunk = n < chunkRays ? n : chunkRays;
+    int rc = ensure_staging(s, chunk);
+    if (rc != TRQ_OK) return rc;
+    uint64_t done = 0; int c = 0;
+    while (done < n) {
+        const uint64_t m = (n - done) < chunk ? (n - done) : chunk;
+        const int b = c % kStageBufs;
+        if (c >= kStageBufs) TRQ_CUDA(cudaStreamWaitEvent(s->sH2D, s->evD2H[b], 0));   // buffer reuse
+        TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, s->sH2D));
+        TRQ_CUDA(cudaEventRecord(s->evH2D[b], s->sH2D));
+        TRQ_CUDA(cudaStreamWaitEvent(s->sCompute, s->evH2D[b], 0));
+        rc = launch_trace(s, s->d_stageRays[b], m, flags, s->d_stageHits[b], s->sCompute);
+        if (rc != TRQ_OK) return rc;
+        TRQ_CUDA(cudaEventRecord(s->evCompute[b], s->sCompute));
+        TRQ_CUDA(cudaStreamWaitEvent(s->sD2H, s->evCompute[b], 0));
+        TRQ_CUDA(cudaMemcpyAsync(hits + done, s->d_stageHits[b], m * sizeof(trq_hit), cudaMemcpyDeviceToHost, s->sD2H));
+        TRQ_CUDA(cudaEventRecord(s->evD2H[b], s->sD2H));
+        done += m; ++c;
+    }
+    TRQ_CUDA(cudaStreamSynchronize(s->sD2H));
+    TRQ_CUDA(cudaStreamSynchronize(s->sCompute));
+    return TRQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int trq_version(void) { return TRQ_VERSION; }
+
+const char* trq_last_error_string(void) { return trq::last_error(); }
+
+int trq_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+uint64_t trq_launch_count(void) { return g_launches.load(); }
+
+int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
+    if (!d || !out) return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: NULL argument");
+    *out = nullptr;
+    if (!d->bvhList || d->nNode == 0) return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: empty bvhList");
+    if ((d->nSphere && !d->sphereList) || (d->nSquare && !d->squareList) || (d->nCube && !d->cubeList) ||
+        (d->nVert && !d->triList) || (d->nTri && !d->idxList))
+        return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: NULL array with non-zero count");
+
+    trq_scene_info_t info{};
+    std::vector<uint32_t> ref;
+    int rc = plan_layout(d, ref, info);                        // pure host validation: runs without a GPU
+    if (rc != TRQ_OK) return rc;
+
+    int ndev = trq_device_count();
+    if (ndev <= 0) return trq::fail(TRQ_ERR_NO_DEVICE, "trq_scene_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: device %d out of range (%d devices)", device, ndev);
+
+    DeviceGuard guard(device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+    trq_scene* s = new (std::nothrow) trq_scene();
+    if (!s) return trq::fail(TRQ_ERR_NOMEM, "trq_scene_create: out of host memory");
+    s->device = device;
+    auto bail = [&](int code) { free_scene(s); return code; };
+
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    s->numSMs = prop.multiProcessorCount;
+
+    if ((rc = upload(&s->d_spheres, d->sphereList, d->nSphere)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_squares, d->squareList, d->nSquare)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_cubes, d->cubeList, d->nCube)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_verts, d->triList, d->nVert)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_idx, d->idxList, (size_t)d->nTri * 3)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_bvh, d->bvhList, d->nNode)) != TRQ_OK) return bail(rc);
+
+    uint32_t* d_ref = nullptr;
+    if ((rc = upload(&d_ref, ref.data(), ref.size())) != TRQ_OK) return bail(rc);
+    auto bail2 = [&](int code) { cudaFree(d_ref); return bail(code); };
+
+    const size_t nodeBytes = (size_t)info.nInterior * 64, triBytes = (size_t)info.nTri * 48, sphBytes = (size_t)info.nSphere * 32;
+    if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes));
+    if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes));
+    if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes));
+    if (cudaMalloc((void**)&s->d_counters, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(counters) failed"));
+
+    {
+        const unsigned block = 256, grid = (d->nNode + block - 1) / block;
+        pack_scene_kernel<<<grid, block>>>(s->d_bvh, d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres,
+                                           s->d_nodes, s->d_tris, s->d_sph);
+        g_launches++;
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "pack_scene_kernel failed: %s", cudaGetErrorString(e)));
+    }
+    cudaFree(d_ref);
+
+    const RefBVH* N = (const RefBVH*)d->bvhList;
+    s->dev.spheres = s->d_spheres; s->dev.squares = s->d_squares; s->dev.cubes = s->d_cubes;
+    s->dev.verts = s->d_verts; s->dev.idx = s->d_idx; s->dev.bvh = s->d_bvh;
+    s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.sph = s->d_sph;
+    s->dev.rootRef = ref[0];
+    for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = N[0].bBOX.mini[k]; s->dev.rootMax[k] = N[0].bBOX.maxi[k]; }
+    s->dev.nNode = d->nNode;
+    s->stackDepth = info.maxDepth + 1;
+
+    info.bytesReferenceLayout = (uint64_t)d->nSphere * sizeof(RefSphere) + (uint64_t)d->nSquare * sizeof(RefSquare) +
+                                (uint64_t)d->nCube * sizeof(RefCube) + (uint64_t)d->nVert * sizeof(RefVertex) +
+                                (uint64_t)d->nTri * 12 + (uint64_t)d->nNode * sizeof(RefBVH);
+    info.bytesPacked = nodeBytes + triBytes + sphBytes;
+    info.device = device;
+    s->info = info;
+    *out = s;
+    return TRQ_OK;
+}
+
+int trq_scene_destroy(trq_scene* s) {
+    if (!s) return TRQ_OK;
+    DeviceGuard guard(s->device);
+    free_scene(s);
+    return TRQ_OK;
+}
+
+int trq_scene_info(const trq_scene* s, trq_scene_info_t* info) {
+    if (!s || !info) return trq::fail(TRQ_ERR_INVALID, "trq_scene_info: NULL argument");
+    *info = s->info;
+    return TRQ_OK;
+}
+
+int trq_trace(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits, void* stream) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_trace: NULL scene");
+    if (n == 0) return TRQ_OK;
+    if (!rays || !hits) return trq::fail(TRQ_ERR_INVALID, "trq_trace: NULL rays/hits");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    if (flags & TRQ_HOST_PTRS) return trace_host(s, rays, n, flags, hits);
+    return launch_trace(s, rays, n, flags, hits, (cudaStream_t)stream);
+}
+
+int trq_expand_hits(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, uint32_t flags,
+                    trq_hit_record* records, void* stream) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_expand_hits: NULL scene");
+    if (n == 0) return TRQ_OK;
+    if (!rays || !hits || !records) return trq::fail(TRQ_ERR_INVALID, "trq_expand_hits: NULL argument");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    const unsigned block = 256;
+    const uint64_t grid = (n + block - 1) / block;
+    if (flags & TRQ_HOST_PTRS) {
+        trq_ray* dr = nullptr; trq_hit* dh = nullptr; trq_hit_record* dq = nullptr;
+        TRQ_CUDA(cudaMalloc((void**)&dr, n * sizeof(trq_ray)));
+        if (cudaMalloc((void**)&dh, n * sizeof(trq_hit)) != cudaSuccess) { cudaFree(dr); return trq::fail(TRQ_ERR_CUDA, "cudaMalloc failed"); }
+        if (cudaMalloc((void**)&dq, n * sizeof(trq_hit_record)) != cudaSuccess) { cudaFree(dr); cudaFree(dh); return trq::fail(TRQ_ERR_CUDA, "cudaMalloc failed"); }
+        cudaError_t e = cudaMemcpy(dr, rays, n * sizeof(trq_ray), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dh, hits, n * sizeof(trq_hit), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { expand_hits_kernel<<<(unsigned)grid, block>>>(s->dev, dr, dh, dq, n); g_launches++; e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaMemcpy(records, dq, n * sizeof(trq_hit_record), cudaMemcpyDeviceToHost);
+        cudaFree(dr); cudaFree(dh); cudaFree(dq);
+        if (e != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "trq_expand_hits: %s", cudaGetErrorString(e));
+        return TRQ_OK;
+    }
+    expand_hits_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(s->dev, rays, hits, records, n);
+    g_launches++;
+    TRQ_CUDA(cudaGetLastError());
+    return TRQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference's ray-query interface, over the C-ABI.
+
+  reference                                             here
+  ----------------------------------------------------  ---------------------------------
+  struct Primitive  (Render.hh:122-130)                 Primitive (six numpy arrays, reference layouts)
+  BVH::buildNode / BVH::buildTree (BVH.hh:246-314)      BVHBuilder.buildNode / buildNodesTriangles / buildTree
+  Scene { primitives }; scene.hit(ray, rec, test_t, any) (Render.hh:132-252)
+                                                        Scene(primitives).hit(rays, any=False)  -- a BATCH of rays
+
+Rays / hits live in device memory as torch tensors of shape (n, 8) float32 (32-byte trq_ray /
+trq_hit rows), or in host memory as numpy structured arrays (`ray_dtype` / `hit_dtype`), in which
+case the library stages the copies itself (TRQ_HOST_PTRS). All compute happens in the CUDA
+kernels behind trq_trace; nothing here falls back to the CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import layout as L
+from ._lib import SceneDesc, SceneInfo, check, lib
+
+
+def _ptr(a):
+    return None if a is None or a.size == 0 else a.ctypes.data
+
+
+class Primitive:
+    """The six arrays of `struct Primitive` (Render.hh:122-130), reference byte layouts."""
+
+    def __init__(self, sphereList=None, squareList=None, cubeList=None, triList=None, idxList=None, bvhList=None):
+        def arr(a, dt):
+            if a is None:
+                return np.zeros(0, dtype=dt)
+            a = np.ascontiguousarray(a)
+            if a.dtype != dt:
+                raise TypeError(f"expected dtype {dt}, got {a.dtype}")
+            return a
+        self.sphereList = arr(sphereList, L.sphere_dtype)
+        self.squareList = arr(squareList, L.square_dtype)
+        self.cubeList = arr(cubeList, L.cube_dtype)
+        self.triList = arr(triList, L.vertex_dtype)
+        self.idxList = arr(None if idxList is None else np.asarray(idxList).reshape(-1), np.dtype("<u4"))
+        self.bvhList = arr(bvhList, L.bvh_dtype)
+
+    @property
+    def nTri(self):
+        return self.idxList.size // 3
+
+    def desc(self):
+        d = SceneDesc()
+        d.sphereList, d.nSphere = _ptr(self.sphereList), self.sphereList.size
+        d.squareList, d.nSquare = _ptr(self.squareList), self.squareList.size
+        d.cubeList, d.nCube = _ptr(self.cubeList), self.cubeList.size
+        d.triList, d.nVert = _ptr(self.triList), self.triList.size
+        d.idxList, d.nTri = _ptr(self.idxList), self.nTri
+        d.bvhList, d.nNode = _ptr(self.bvhList), self.bvhList.size
+        return d
+
+    def nbytes(self):
+        return sum(a.nbytes for a in (self.sphereList, self.squareList, self.cubeList, self.triList, self.idxList, self.bvhList))
+
+
+class BVHBuilder:
+    """BVH::buildNode / BVH::buildTree (BVH.hh:246-314): leaves are appended, then the tree is built."""
+
+    def __init__(self):
+        self._chunks = []
+
+    def buildNode(self, box_min, box_max, model_matrix, pType, pIndex):
+        node = np.zeros(1, dtype=L.bvh_dtype)
+        lo = np.ascontiguousarray(box_min, dtype=np.float32)
+        hi = np.ascontiguousarray(box_max, dtype=np.float32)
+        m = None if model_matrix is None else np.ascontiguousarray(model_matrix, dtype=np.float32).reshape(16)
+        check(lib.trq_bvh_build_node(lo.ctypes.data, hi.ctypes.data, None if m is None else m.ctypes.data,
+                                     int(pType), int(pIndex), node.ctypes.data), "trq_bvh_build_node")
+        self._chunks.append(node)
+
+    def buildNodesTriangles(self, triList, idxList, pIndexBase=0):
+        idx = np.ascontiguousarray(np.asarray(idxList).reshape(-1), dtype="<u4")
+        n = idx.size // 3
+        nodes = np.zeros(n, dtype=L.bvh_dtype)
+        if n:
+            check(lib.trq_bvh_build_nodes_triangles(triList.ctypes.data, idx.ctypes.data, n, int(pIndexBase),
+                                                    nodes.ctypes.data), "trq_bvh_build_nodes_triangles")
+        self._chunks.append(nodes)
+
+    def buildTree(self):
+        leaves = np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=L.bvh_dtype)
+        n = leaves.size
+        if n == 0:
+            raise ValueError("buildTree: no leaves")
+        nodes = np.zeros(2 * n - 1, dtype=L.bvh_dtype)
+        nodes[:n] = leaves
+        nNode, depth = C.c_uint32(0), C.c_uint32(0)
+        check(lib.trq_bvh_build_tree(nodes.ctypes.data, n, C.byref(nNode), C.byref(depth)), "trq_bvh_build_tree")
+        self.maxDepth = depth.value
+        return nodes[: nNode.value]
+
+
+class Scene:
+    """`Scene { primitives }` (Render.hh:132-134), resident on one GPU."""
+
+    def __init__(self, primitives, device=0):
+        self.primitives = primitives
+        self._h = C.c_void_p(None)
+        d = primitives.desc()
+        check(lib.trq_scene_create(C.byref(d), int(device), C.byref(self._h)), "trq_scene_create")
+        self.device = int(device)
+        info = SceneInfo()
+        check(lib.trq_scene_info(self._h, C.byref(info)), "trq_scene_info")
+        self.info = {k: getattr(info, k) for k, _ in SceneInfo._fields_ if k != "pad"}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.trq_scene_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    __del__ = close
+
+    # ---- Scene::hit over a batch ------------------------------------------------------------
+    def hit(self, rays, any=False, out=None, reflayout=False, stream=None):
+        """rays: torch CUDA float32 tensor (n, 8) -> returns torch CUDA float32 tensor (n, 8) holding
+        trq_hit rows (view as int32 for the id fields); or numpy `ray_dtype` array -> numpy `hit_dtype`."""
+        flags = (L.TRACE_ANY if any else 0) | (L.KERNEL_REFLAYOUT if reflayout else 0)
+        if isinstance(rays, np.ndarray):
+            if rays.dtype != L.ray_dtype:
+                raise TypeError("host rays must have ray_dtype")
+            rays = np.ascontiguousarray(rays)
+            hits = out if out is not None else np.empty(rays.size, dtype=L.hit_dtype)
+            check(lib.trq_trace(self._h, rays.ctypes.data, rays.size, flags | L.HOST_PTRS, hits.ctypes.data, None), "trq_trace")
+            return hits
+        import torch
+        if not (rays.is_cuda and rays.dtype == torch.float32 and rays.dim() == 2 and rays.shape[1] == 8 and rays.is_contiguous()):
+            raise TypeError("device rays must be a contiguous CUDA float32 tensor of shape (n, 8)")
+        if rays.device.index != self.device:
+            raise ValueError("rays are on a different device than the scene")
+        n = rays.shape[0]
+        hits = out if out is not None else torch.empty((n, 8), dtype=torch.float32, device=rays.device)
+        st = stream if stream is not None else torch.cuda.current_stream(rays.device).cuda_stream
+        check(lib.trq_trace(self._h, rays.data_ptr(), n, flags, hits.data_ptr(), C.c_void_p(st)), "trq_trace")
+        return hits
+
+    def hit_host(self, rays_ptr, n, hits_ptr, any=False):
+        """Raw host-pointer call (pinned buffers owned by the caller); used by the e2e bench."""
+        flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS
+        check(lib.trq_trace(self._h, rays_ptr, n, flags, hits_ptr, None), "trq_trace")
+
+    def expand(self, rays, hits, out=None, stream=None):
+        """trq_expand_hits: HitRecord fields (p, gn, sn, uv, f, material) for the hits of `rays`."""
+        if isinstance(rays, np.ndarray):
+            recs = out if out is not None else np.empty(rays.size, dtype=L.record_dtype)
+            check(lib.trq_expand_hits(self._h, rays.ctypes.data, hits.ctypes.data, rays.size, L.HOST_PTRS,
+                                      recs.ctypes.data, None), "trq_expand_hits")
+            return recs
+        import torch
+        n = rays.shape[0]
+        recs = out if out is not None else torch.empty((n, 16), dtype=torch.float32, device=rays.device)
+        st = stream if stream is not None else torch.cuda.current_stream(rays.device).cuda_stream
+        check(lib.trq_expand_hits(self._h, rays.data_ptr(), hits.data_ptr(), n, 0, recs.data_ptr(), C.c_void_p(st)),
+              "trq_expand_hits")
+        return recs
+
+
+def hits_to_numpy(hits):
+    """torch (n, 8) float32 hit tensor -> numpy structured `hit_dtype` array (host copy)."""
+    return hits.detach().cpu().numpy().view(L.hit_dtype).reshape(-1)
+
+
+def rays_to_torch(rays, device):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(rays).view(np.float32).reshape(-1, 8)).to(device)
+
+
+def launch_count():
+    return int(lib.trq_launch_count())
