@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Build (or reuse) the product library and the oracle libraries once per session."""
+    import __graft_entry__ as g
+    g.build()
+    return True
+
+
+@pytest.fixture(scope="session")
+def port(built):
+    from oracle.pyoracle import Port
+    return Port()
+
+
+@pytest.fixture(scope="session")
+def reference(built):
+    from oracle.pyoracle import Reference
+    if not Reference.available():
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    return Reference()
