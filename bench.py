@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ray-query hot path (contract: see DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c3|c2|c4|c5|soup1m] [--impl reference]
+
+A "step" is one pass of the hot path (trq_trace, closest-hit) over one batch of synthetic rays of the
+named BASELINE config. Default workload = C3 (the config the north_star target is quoted on): the
+~1.0 M-triangle "meshes" scene (coatball + teapot subdivided twice inside the Cornell box) traced with
+the incoherent diffuse-bounce rays spawned from the 3840x2160 primary hits.
+
+  value   whole-job Mrays/s, rays and hit buffers resident in HBM, CUDA events, max over ranks
+  e2e     the same metric through the C-ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+  roofline  traversal kernel only: algorithmic bytes (instrumented-oracle step counts, SURVEY 8d formula)
+            / its CUDA-event duration, against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's own Scene::hit (oracle/_ref, compiled verbatim) on the host cores, on a
+            bounded strided sample of the same rays (N=1, rank 0 only)
+
+`--impl reference` times that CPU reference alone (rank 0; other ranks exit).
+Multi-GPU: one process per GPU (torchrun), scene broadcast from rank 0 over NCCL, rays sharded by batch
+(each rank traces its own bounce-ray batch: weak scaling), no collective on the data path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/sec closest-hit"
+UNIT = "Mrays/s"
+HBM_FALLBACK_GBS = 6650.0
+
+WORKLOADS = {
+    "c2": "C2: RT_Metal Cornell box triangles + teapot (15.7k tris), 1920x1080 primary hits -> 1 diffuse bounce batch",
+    "c3": "C3: RT_Metal meshes scene (coatball+teapot subdivided x16, 1.0M tris), incoherent diffuse bounce rays from 3840x2160 primary hits",
+    "c4": "C4: C3 geometry + 10,012 spheres, any-hit shadow rays toward light squares 5/6 from 3840x2160 primary hits",
+    "c5": "C5: 10M-triangle random soup, 8M uniform incoherent rays per GPU",
+    "soup1m": "1M-triangle random soup, 8M uniform incoherent rays",
+}
+# algorithmic bytes per ray measured once by the instrumented oracle; used only if the
+# oracle cannot be run in this process. Recomputed live on the cpu_baseline sample otherwise.
+BYTES_PER_RAY_FALLBACK = {"c2": 1094.0, "c3": 1795.0, "c4": 1000.0, "c5": 8000.0, "soup1m": 7029.0}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------- workloads
+def build_scene(name):
+    from tracer_b200 import harness as H
+    if name == "c2":
+        return H.scene_c2()
+    if name == "c3":
+        return H.scene_c3(2)
+    if name == "c4":
+        return H.scene_c4(2)
+    if name == "c5":
+        return H.scene_soup(10_000_000, seed=1, extent=0.004)
+    if name == "soup1m":
+        return H.scene_soup(1_000_000, seed=1, extent=0.01)
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_rays_gpu(name, prim, scene, rank, device):
+    """Ray batch of this rank for the named workload (generation is not timed)."""
+    from tracer_b200 import harness as H, layout as L, rays_to_torch
+    if name in ("c5", "soup1m"):
+        n = 8_000_000
+        return H.random_rays(n, seed=2, first=rank * n), False
+    W, Hh = (1920, 1080) if name == "c2" else (3840, 2160)
+    primary = H.cornell_camera_rays(W, Hh)
+    d = rays_to_torch(primary, device)
+    recs = scene.expand(d, scene.hit(d)).cpu().numpy().view(L.record_dtype).reshape(-1)
+    seed_base = rank << 32
+    if name == "c4":
+        la, lb = H.scene_c4_lights(prim)
+        rays, _ = H.shadow_rays(recs, la, lb, seed_base)
+        return rays, True
+    rays, _ = H.bounce_rays(recs, seed_base)
+    return rays, False
+
+
+def make_rays_cpu_sample(name, prim, ref_trace_records, stride):
+    """Strided sample of the same workload generated WITHOUT the GPU (reference arm): primary pixels are
+    subsampled by `stride`, their hits come from the CPU reference, bounce/shadow rays are spawned from those."""
+    from tracer_b200 import harness as H
+    if name in ("c5", "soup1m"):
+        return H.random_rays(8_000_000 // stride, seed=2), False
+    W, Hh = (1920, 1080) if name == "c2" else (3840, 2160)
+    primary = H.cornell_camera_rays(W, Hh)[::stride].copy()
+    recs = ref_trace_records(primary)
+    if name == "c4":
+        la, lb = H.scene_c4_lights(prim)
+        return H.shadow_rays(recs, la, lb, 0)[0], True
+    return H.bounce_rays(recs, 0)[0], False
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="trq_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        self.t0 = self.t1 = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            # "under load": the upper half of the samples (the sampler also sees idle time around the region)
+            load = sorted(sm)[len(sm) // 2:]
+            out.update({"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)})
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- CPU reference
+def cpu_reference(prim, rays, any_hit, budget_s, nthreads):
+    """Time the reference's Scene::hit (verbatim build if present, else the C port) on `rays` subsampled so that one
+    pass takes about budget_s. Returns (Mrays/s, kind, cores, sample description, bytes_per_ray or None)."""
+    from oracle.pyoracle import Port, Reference
+    port = Port()
+    use_ref = Reference.available()
+    ref = Reference() if use_ref else None
+
+    def run(sub):
+        t = time.perf_counter()
+        if use_ref:
+            ref.trace_lite(prim, sub, any=any_hit, nthreads=nthreads)
+        else:
+            port.trace(prim, sub, any=any_hit, nthreads=nthreads)
+        return time.perf_counter() - t
+
+    pilot = rays[:: max(1, rays.size // 40000)]
+    run(pilot[: max(1, pilot.size // 4)])                       # page in
+    dt = run(pilot)
+    rate = pilot.size / max(dt, 1e-6)
+    want = int(min(rays.size, max(pilot.size, rate * budget_s)))
+    stride = max(1, rays.size // want)
+    sub = np.ascontiguousarray(rays[::stride])
+    dt = run(sub)
+    tot = port.trace(prim, pilot, any=any_hit, nthreads=nthreads)["totals"]      # step counters (not timed)
+    bpr = tot["bytes"] / max(1, tot["n_rays"])
+    kind = "reference" if use_ref else "port"
+    sample = f"every {stride}th ray of the batch ({sub.size} rays, {dt:.1f} s)"
+    return sub.size / dt / 1e6, kind, nthreads, sample, bpr, sub
+
+
+# ----------------------------------------------------------------------------------------------- arms
+def run_reference_arm(a):
+    rank, _, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    if rank != 0:
+        return 0
+    from oracle.pyoracle import Port, Reference
+    prim = build_scene(a.workload)
+    nthreads = os.cpu_count() or 1
+    use_ref = Reference.available()
+    eng = Reference() if use_ref else Port()
+    rec_fn = (lambda r: eng.trace(prim, r, nthreads=nthreads)) if use_ref else (lambda r: eng.trace(prim, r, records=True, nthreads=nthreads)["records"])
+    rays, any_hit = make_rays_cpu_sample(a.workload, prim, rec_fn, stride=16)
+
+    def run(sub):
+        t = time.perf_counter()
+        if use_ref:
+            eng.trace_lite(prim, sub, any=any_hit, nthreads=nthreads)
+        else:
+            eng.trace(prim, sub, any=any_hit, nthreads=nthreads)
+        return time.perf_counter() - t
+
+    pilot = rays[:: max(1, rays.size // 20000)]
+    rate = pilot.size / max(run(pilot), 1e-6)
+    budget = min(3.0, 120.0 / max(1, a.steps + a.warmup))
+    stride = max(1, int(rays.size / max(pilot.size, rate * budget)))
+    sub = np.ascontiguousarray(rays[::stride])
+    for _ in range(a.warmup):
+        run(sub)
+    t = sum(run(sub) for _ in range(a.steps))
+    v = sub.size * a.steps / t / 1e6
+    kind = "reference" if use_ref else "port"
+    sample = f"{sub.size} rays per step: every {16 * stride}th ray of the batch (primary pixels subsampled x16, then stride {stride})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": round(t / a.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(a.workload),
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
+        "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def config_of(workload, extra=None):
+    c = {"workload": WORKLOADS[workload], "query": "any-hit" if workload == "c4" else "closest-hit",
+         "sharding": "ray batch per rank, scene replicated"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+def run_gpu_arm(a):
+    import torch
+
+    from tracer_b200 import Scene, dist as D, launch_count, rays_to_torch
+    rank, local_rank, world = D.init()
+    if world != a.gpus:
+        log(f"warning: --gpus {a.gpus} but WORLD_SIZE={world}")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+
+    t0 = time.time()
+    prim = build_scene(a.workload) if rank == 0 else None
+    t_build = time.time() - t0
+    prim = D.replicate_primitive(prim, src=0)
+    scene = Scene(prim, local_rank)
+    rays, any_hit = make_rays_gpu(a.workload, prim, scene, rank, device)
+    n = rays.size
+    d_rays = rays_to_torch(rays, device)
+    d_hits = torch.empty((n, 8), dtype=torch.float32, device=device)
+    if rank == 0:
+        log(f"# scene {scene.info}, build {t_build:.1f}s, {n} rays/rank")
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if a.flush_l2 else None
+
+    def step():
+        scene.hit(d_rays, any=any_hit, out=d_hits)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device events, barrier + synchronize on both sides
+    scene.profile(True)
+    sampler = ClockSampler(local_rank)
+    launches0 = launch_count()
+    D.barrier(); torch.cuda.synchronize()
+    total_ms = 0.0
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        total_ms = e0.elapsed_time(e1)
+    else:
+        evs = []
+        for _ in range(a.steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        total_ms = sum(x.elapsed_time(y) for x, y in evs)
+    D.barrier()
+    launches = launch_count() - launches0
+    clocks = sampler.stop()
+    nl, trace_ms, resolve_ms = scene.profile_read()
+    scene.profile(False)
+    total_ms = D.max_over_ranks(total_ms)
+    total_rays = D.sum_over_ranks(n)
+    value = total_rays * a.steps / total_ms / 1e3
+
+    # ---- e2e: host (pinned) rays in, host hits out, through the C-ABI host-pointer path
+    h_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).pin_memory()
+    h_hits = torch.empty((n, 8), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(a.steps, 20))
+    for _ in range(2):
+        scene.hit_host(h_rays.data_ptr(), n, h_hits.data_ptr(), any=any_hit)
+    D.barrier(); torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(e2e_steps):
+        scene.hit_host(h_rays.data_ptr(), n, h_hits.data_ptr(), any=any_hit)
+    torch.cuda.synchronize()
+    e2e_s = D.max_over_ranks(time.perf_counter() - t)
+    e2e_value = total_rays * e2e_steps / e2e_s / 1e6
+    # the host path must produce the same bytes as the device path
+    same = bool(torch.equal(h_hits, d_hits.cpu()))
+    hit_frac = float((d_hits[:, 7].view(torch.int32) & 1).float().mean())
+
+    # ---- multi-GPU: scene checksum agreement + gathered hit count (not timed)
+    gathered = None
+    if world > 1:
+        cs = D.checksum_primitive(prim)
+        lo, hi = D.max_over_ranks(float(cs % (1 << 52))), -D.max_over_ranks(-float(cs % (1 << 52)))
+        assert lo == hi, "scene broadcast checksum differs across ranks"
+        parts = D.gather_hits(d_hits[: min(n, 1 << 20)])
+        gathered = int(sum(p.shape[0] for p in parts))
+
+    if rank != 0:
+        return 0
+
+    # ---- CPU baseline + algorithmic bytes (rank 0, N=1 only for the baseline)
+    peak, peak_src = peaks()
+    bpr, cpu = BYTES_PER_RAY_FALLBACK[a.workload], None
+    try:
+        if world == 1 and not a.no_cpu_baseline:
+            v, kind, cores, sample, bpr, sub = cpu_reference(prim, rays, any_hit, a.cpu_budget, os.cpu_count() or 1)
+            cpu = {"value": round(v, 4), "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+            # parity spot-check on the timed sample: GPU hits of the sample rays vs the oracle
+            from oracle.pyoracle import Port
+            chk = sub[:: max(1, sub.size // 100000)]
+            want = Port().trace(prim, chk, any=any_hit, nthreads=cores)["hits"]
+            got = scene.hit(rays_to_torch(chk, device), any=any_hit).cpu().numpy().view(want.dtype).reshape(-1)
+            ids_ok = all(np.array_equal(got[k], want[k]) for k in ("flags", "pType", "pIndex", "leafNode"))
+            t_ok = np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+            cpu["parity_on_sample"] = {"rays": int(chk.size), "ids_bit_exact": bool(ids_ok), "t_bit_exact": bool(t_ok)}
+        else:
+            from oracle.pyoracle import Port
+            pilot = rays[:: max(1, n // 40000)]
+            tot = Port().trace(prim, pilot, any=any_hit, nthreads=os.cpu_count() or 1)["totals"]
+            bpr = tot["bytes"] / tot["n_rays"]
+    except Exception as e:  # the oracle is test infrastructure: never let it take the GPU numbers down
+        log(f"# cpu baseline unavailable: {e!r}")
+
+    trace_ms_avg = trace_ms / max(1, nl)
+    achieved = bpr * n / (trace_ms_avg * 1e-3) / 1e9 if trace_ms_avg > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(a.workload)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": round(total_ms / a.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": config_of(a.workload, {
+            "rays_per_step_per_gpu": int(n), "triangles": int(prim.nTri), "bvh_nodes": int(prim.bvhList.size),
+            "hit_fraction": round(hit_frac, 4),
+            "l2": ("flushed between steps (256 MB write)" if a.flush_l2 else
+                   f"no flush: rays+hits stream {2 * n * 32 / 1e6:.0f} MB per step (> 126 MB L2)"),
+        }),
+        "roofline": {"bound": "hbm", "kernel": "trace_packed_kernel", "achieved": None if achieved is None else round(achieved, 1),
+                     "peak": peak, "unit": "GB/s", "frac": None if achieved is None else round(achieved / peak, 4),
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_ray": round(bpr, 1),
+                     "kernel_ms": round(trace_ms_avg, 4), "resolve_kernel_ms": round(resolve_ms / max(1, nl), 4),
+                     "kernel_share_of_step": round(trace_ms_avg / max(1e-9, total_ms / a.steps), 4)},
+        "cpu_baseline": cpu,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 32),
+                "steps": e2e_steps, "host_path_equals_device_path": same, "timing": "wall clock around K synchronous C-ABI calls, max over ranks"},
+        "gpu_launches": int(launches),
+        "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
+    }
+    if gathered is not None:
+        line["gathered_hits_checked"] = gathered
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--flush-l2", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+    return run_gpu_arm(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

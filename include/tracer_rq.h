@@ -141,6 +141,13 @@ int  trq_trace(trq_scene* scene, const trq_ray* rays, uint64_t n, uint32_t flags
 int  trq_expand_hits(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n,
                      uint32_t flags, trq_hit_record* records, void* stream);
 
+/* Per-kernel timing for roofline reports: when enabled, every device-pointer trq_trace records CUDA
+ * events (on the caller's stream) around the traversal kernel and around the resolve kernel.
+ * trq_profile_read waits for them and returns the SUMS over the launches since the last read
+ * (at most the 64 most recent) and resets. Not for TRQ_HOST_PTRS calls. */
+int  trq_profile_enable(trq_scene* scene, int on);
+int  trq_profile_read(trq_scene* scene, uint32_t* nLaunches, float* traceKernelMs, float* resolveKernelMs);
+
 /* Number of kernel launches issued by this library in this process (bench evidence). */
 uint64_t trq_launch_count(void);
 

@@ -1,0 +1,103 @@
+"""CPU: the sequential restatement of BVH::buildNode / make / buildTree (BVH.hh:35-314). The reference builder
+cannot be compiled here (clang blocks + libdispatch), so it is pinned by the structural contract the ray query
+relies on and by brute force: the closest hit found through the tree equals the closest hit over all primitives."""
+import numpy as np
+import pytest
+
+from tracer_b200 import harness as H, layout as L
+from tracer_b200._lib import ERR_DEPTH, ERR_INVALID, TrqError, lib
+
+
+def check_tree(bvh, n_leaves):
+    assert bvh.size == 2 * n_leaves - 1
+    if n_leaves == 1:
+        assert bvh[0]["pType"] != L.BVH and bvh[0]["parent"] == 0
+        return 0
+    assert bvh[0]["pType"] == L.BVH and bvh[0]["parent"] == 0                       # root at 0 (BVH.hh:263-268)
+    leaves = bvh[1:n_leaves + 1]
+    assert (leaves["pType"] != L.BVH).all() and (leaves["left"] == 0).all() and (leaves["right"] == 0).all()
+    inter = np.concatenate([[0], np.arange(n_leaves + 1, bvh.size)])
+    assert (bvh[inter]["pType"] == L.BVH).all()
+    l, r = bvh[inter]["left"], bvh[inter]["right"]
+    assert np.array_equal(bvh[l]["parent"], inter) and np.array_equal(bvh[r]["parent"], inter)
+    kids = np.concatenate([l, r])
+    assert np.array_equal(np.sort(kids), np.arange(1, bvh.size))                    # every non-root node is a child exactly once
+    # parent box = union of child boxes, exactly (fminf / fmaxf)
+    assert np.array_equal(bvh[inter]["mini"], np.minimum(bvh[l]["mini"], bvh[r]["mini"]))
+    assert np.array_equal(bvh[inter]["maxi"], np.maximum(bvh[l]["maxi"], bvh[r]["maxi"]))
+    assert (bvh[inter]["axis"] <= 2).all()
+    depth = np.zeros(bvh.size, dtype=np.int64)
+    for i in inter[1:][::-1]:                                                        # parents have larger indices (post-order)
+        depth[i] = depth[bvh[i]["parent"]] + 1
+    return int(depth.max())
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 100, 5000])
+def test_structure_soup(built, n):
+    prim = H.scene_soup(n, seed=n, extent=0.1)
+    d = check_tree(prim.bvhList, n)
+    assert d <= 31
+    tri_leaf = prim.bvhList[prim.bvhList["pType"] == L.TRIANGLE]
+    assert np.array_equal(np.sort(tri_leaf["pIndex"]), np.arange(n))
+    v = prim.triList["v"][prim.idxList.reshape(-1, 3)]                               # leaf box = min/max of the 3 vertices
+    order = np.argsort(tri_leaf["pIndex"])
+    assert np.array_equal(tri_leaf["mini"][order], v.min(1)) and np.array_equal(tri_leaf["maxi"][order], v.max(1))
+
+
+def test_structure_mixed_and_meshes(built):
+    prim = H.scene_reference_cornell()
+    n = (prim.bvhList["pType"] != L.BVH).sum()
+    check_tree(prim.bvhList, n)
+    # leaf creation order of AAPLRenderer.mm:454-468,546-591: spheres, cubes, squares, triangles
+    types = prim.bvhList[1:n + 1]["pType"]
+    assert list(types[:12]) == [L.SPHERE] * 12 and list(types[12:14]) == [L.CUBE] * 2 and list(types[14:21]) == [L.SQUARE] * 7
+    assert (types[21:] == L.TRIANGLE).all()
+    c2 = H.scene_c2()
+    assert check_tree(c2.bvhList, c2.nTri) <= 31
+
+
+def test_identical_centroids_fall_back_to_median_split(built):
+    """All centroids equal: relative() is 0/0, every SAH cost is NaN, the partition is empty and the sort+median
+    fallback (BVH.hh:187-195) must still produce a valid tree."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    ms = H.MeshSoup()
+    for _ in range(33):
+        ms.add(pos, [[0, 1, 2]])
+    tri, idx = ms.arrays()
+    prim = H.build_primitive(tri, idx)
+    assert check_tree(prim.bvhList, 33) <= 31
+
+
+def test_deterministic(built):
+    a = H.scene_soup(3000, seed=5, extent=0.05).bvhList
+    b = H.scene_soup(3000, seed=5, extent=0.05).bvhList
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def test_errors(built):
+    import ctypes as C
+    n, d = C.c_uint32(0), C.c_uint32(0)
+    assert lib.trq_bvh_build_tree(None, 4, C.byref(n), C.byref(d)) == ERR_INVALID
+    node = np.zeros(1, dtype=L.bvh_dtype)
+    assert lib.trq_bvh_build_tree(node.ctypes.data, 0, C.byref(n), C.byref(d)) == ERR_INVALID
+    assert b"empty" in lib.trq_last_error_string()
+
+
+def test_tree_finds_the_brute_force_closest_hit(built, port):
+    """Independent check of builder + traversal: for every ray, t through the BVH == min t over ALL triangles
+    tested one by one with the same intersector (ids may differ only on exact ties)."""
+    prim = H.scene_soup(400, seed=21, extent=0.3)
+    rays = H.random_rays(1500, seed=22)
+    got = port.trace(prim, rays)["hits"]
+    idx = prim.idxList.reshape(-1, 3)
+    for i in range(0, rays.size, 3):
+        best = np.float32(L.FLT_MAX)
+        for k in range(len(idx)):
+            r = np.array([L.FLT_MIN, best], dtype=np.float32)
+            h, r2, _, _ = port.triangle_hit(prim.triList, idx[k], rays["o"][i], rays["d"][i], r)
+            if h:
+                best = r2[1]
+        if best < L.FLT_MAX:
+            assert (got["flags"][i] & 1) and got["t"][i] == best
+        else:
+            assert not (got["flags"][i] & 1)

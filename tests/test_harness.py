@@ -1,0 +1,74 @@
+"""CPU: the workload generators (csrc/host/harness.cpp) against the reference functions they restate."""
+import numpy as np
+
+from tracer_b200 import harness as H, layout as L
+from tracer_b200._lib import lib
+
+from .util import bits
+
+
+def test_pcg32_known_answer():
+    """pcg32_srandom(42, 54): the upstream pcg-c-basic demo sequence (Random.metal:3-19 == pcg_basic.c:44-67)."""
+    out = np.zeros(6, dtype=np.uint32)
+    lib.trqh_pcg32_fill_u32(42, 54, 6, out.ctypes.data)
+    assert [hex(x) for x in out] == ["0xa15c02b7", "0x7b47f409", "0xba1d3330", "0x83d2f293", "0xbfa4784b", "0xcbed606e"]
+    f = H.pcg32_floats(42, 54, 6)
+    assert np.array_equal(f, np.ldexp(out.astype(np.float32), -32).astype(np.float32)) and (f >= 0).all() and (f <= 1).all()
+
+
+def test_camera_rays_are_reference_rays(reference):
+    rays = H.cornell_camera_rays(32, 18)
+    assert np.allclose(np.linalg.norm(rays["d"], axis=1), 1.0, atol=1e-6)
+    assert (rays["o"] == np.array([278, 278, -800], dtype=np.float32)).all() and (rays["tmax"] == np.float32(L.FLT_MAX)).all()
+    # the centre pixel looks down +z; normalisation is the Ray ctor's (three IEEE divides)
+    d = rays["d"][9 * 32 + 16]
+    assert abs(d[0]) < 1e-6 and abs(d[1]) < 1e-6 and d[2] > 0.999
+    o2, d2 = reference.ray_ctor(rays["o"][5], rays["d"][5] * np.float32(3.0))
+    assert np.allclose(d2, rays["d"][5], atol=1e-7)
+
+
+def test_bounce_rays_follow_the_reference_spawn(reference, port):
+    prim = H.scene_reference_cornell()
+    first = reference.trace(prim, H.cornell_camera_rays(48, 27))
+    rays, src = H.bounce_rays(first, seed_base=7)
+    assert rays.size == int(first["hit"].sum()) and np.array_equal(src, np.nonzero(first["hit"])[0].astype(np.uint32))
+    for k in range(0, rays.size, 37):
+        rec = first[src[k]]
+        assert np.array_equal(bits(rays["o"][k]), bits(reference.offset_ray(rec["p"], rec["sn"])))          # Render.metal:450
+        uu = H.pcg32_floats(7 + int(src[k]), 1, 2)
+        nx, ny = reference.coordinate_system(rec["sn"])
+        wi = reference.cosine_sample_hemisphere(uu)
+        want = nx * wi[0] + ny * wi[1] + rec["sn"] * wi[2]
+        want = want / np.linalg.norm(want)
+        assert np.allclose(rays["d"][k], want, atol=2e-6)
+        assert np.dot(rays["d"][k], rec["sn"]) >= -1e-6                                                        # into the hemisphere of sn
+
+
+def test_shadow_rays_point_at_the_lights(reference):
+    prim = H.scene_reference_cornell()
+    first = reference.trace(prim, H.cornell_camera_rays(48, 27))
+    la, lb = prim.squareList[5:6], prim.squareList[6:7]
+    rays, src = H.shadow_rays(first, la, lb, seed_base=3)
+    assert rays.size == int(first["hit"].sum())
+    end = rays["o"] + rays["d"] * rays["tmax"][:, None]
+    on_a = np.abs(end[:, 1] - 554.9) < 0.5
+    on_b = np.abs(end[:, 0] + 300) < 0.5
+    assert (on_a | on_b).all() and on_a.any() and on_b.any()
+    assert np.allclose(np.linalg.norm(rays["d"], axis=1), 1.0, atol=1e-6)
+
+
+def test_random_rays_and_soup_are_deterministic_and_shardable():
+    a = H.random_rays(1000, seed=2)
+    b = np.concatenate([H.random_rays(400, seed=2, first=0), H.random_rays(600, seed=2, first=400)])
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))                     # stream-per-ray => any sharding gives the same rays
+    assert (a["d"] != 0).all() and np.allclose(np.linalg.norm(a["d"], axis=1), 1.0, atol=1e-6)
+    s1, s2 = H.scene_soup(100, seed=1), H.scene_soup(100, seed=1)
+    assert np.array_equal(s1.triList.view(np.uint8), s2.triList.view(np.uint8))
+
+
+def test_subdivide_and_scene_sizes():
+    pos = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=np.float32)
+    p2, t2 = H.subdivide(pos, [[0, 1, 2], [1, 3, 2]], 2)
+    assert len(t2) == 32 and len(p2) == 25                                       # shared edge midpoints
+    c2 = H.scene_c2()
+    assert c2.nTri == 14 + 24 + 15704

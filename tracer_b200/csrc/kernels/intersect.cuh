@@ -41,6 +41,21 @@ __device__ __forceinline__ bool box_hit_t(const f3& mini, const f3& maxi, const 
     return true;
 }
 
+// hit_t specialised for Scene::hit's range_t.x == FLT_MIN (Render.hh:143), same results with fewer
+// instructions: after `tmin = max(tmin, FLT_MIN)` tmin is >= FLT_MIN > 0 for every input (fmaxf drops
+// NaNs), so `tmax < 0` implies `tmax < tmin` and the `tmin < 0 ? tmax : tmin` select always takes tmin.
+__device__ __forceinline__ bool box_entry(const f3& mini, const f3& maxi, const RayCtx& r, float range_y, float& t) {
+    f3 ts = mul3(sub3(mini, r.o), r.inv);
+    f3 te = mul3(sub3(maxi, r.o), r.inv);
+    float tmin = fmaxf(fmaxf(fminf(ts.x, te.x), fminf(ts.y, te.y)), fminf(ts.z, te.z));
+    float tmax = fminf(fminf(fmaxf(ts.x, te.x), fmaxf(ts.y, te.y)), fmaxf(ts.z, te.z));
+    tmin = fmaxf(tmin, FLT_MIN);
+    tmax = fminf(tmax, range_y);
+    if (tmax < tmin) return false;
+    t = tmin;
+    return true;
+}
+
 __device__ __forceinline__ bool box_hit(const f3& mini, const f3& maxi, const RayCtx& r,
                                         float range_x, float range_y) {
     float t;

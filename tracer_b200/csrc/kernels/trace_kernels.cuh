@@ -133,6 +133,7 @@ struct TraceParams {
     unsigned long long* counter;   // global ray queue head
     uint32_t       stackDepth;     // entries per lane
     uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
+    uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
 };
 
 template <bool ANY>
@@ -180,18 +181,26 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         if (actMask == 0u) { if (exhausted) break; else continue; }
 
         // ---- traverse until enough lanes have retired to make a refill worthwhile ----
+        // Two phases per round so that the (rarer) leaf code is not issued on every interior step:
+        //   interior phase: lanes sitting on an interior node step; lanes that reached a leaf wait (a lane
+        //     must test its leaf BEFORE it continues, or pruning/tie order would differ from the reference);
+        //     the phase ends when no lane is on an interior node or enough lanes wait at leaves;
+        //   leaf phase: every waiting lane tests its primitive and pops.
         const int keepGoing = exhausted ? 0 : (32 - (int)P.refillMin);
         do {
-            if (active) {
-                const uint32_t kind = TRQ_REF_KIND(cur);
-                if (kind == REF_INTERIOR) {
+            for (;;) {
+                const bool onInterior = active && TRQ_REF_KIND(cur) == REF_INTERIOR;
+                const int nInt = __popc(__ballot_sync(0xffffffffu, onInterior));
+                const int nWait = __popc(__ballot_sync(0xffffffffu, active && !onInterior));
+                if (nInt == 0 || nWait >= (int)P.leafBatch || nWait > nInt) break;
+                if (onInterior) {
                     const float4* np = S.nodes + (size_t)TRQ_REF_INDEX(cur) * 4u;
                     float4 q0, q1, q2, q3;
                     ldg8(np, q0, q1);
                     ldg8(np + 2, q2, q3);
                     float tl = range_y, tr = range_y;                     // :157
-                    const bool lt = box_hit_t(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ray, FLT_MIN, range_y, tl);
-                    const bool rt = box_hit_t(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ray, FLT_MIN, range_y, tr);
+                    const bool lt = box_entry(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ray, range_y, tl);   // :159
+                    const bool rt = box_entry(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ray, range_y, tr);   // :160
                     const uint32_t lref = __float_as_uint(q0.w), rref = __float_as_uint(q1.w);
                     if (!lt && !rt) {                                     // :162-169  pop
                         if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * TRQ_BLOCK]; }
@@ -200,7 +209,16 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                         if (lt && rt) { stk[sp * TRQ_BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
                         cur = selLeft ? lref : rref;
                     }
-                } else {
+                    if (cur == TRQ_REF_DONE_WORD) {
+                        const bool hit = (range_y < test_t) && best != 0xffffffffu;   // :251
+                        store_compact(P.hits, rayIdx, hit, range_y, best, bu, bv, aux);
+                        active = false;
+                    }
+                }
+            }
+            if (active) {
+                const uint32_t kind = TRQ_REF_KIND(cur);
+                if (kind != REF_INTERIOR) {
                     bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t leaf = 0, a = 0;
                     if (kind == REF_TRI) {
                         const float4* tp = S.tris + (size_t)TRQ_REF_INDEX(cur) * 3u;

@@ -46,6 +46,7 @@ struct DeviceGuard {
 
 constexpr int kCounterRing = 256;
 constexpr int kStageBufs = 3;
+constexpr int kProfRing = 64;
 
 }  // namespace
 
@@ -77,6 +78,10 @@ struct trq_scene {
     cudaStream_t sH2D = nullptr, sCompute = nullptr, sD2H = nullptr;
     cudaEvent_t evH2D[kStageBufs] = {}, evCompute[kStageBufs] = {}, evD2H[kStageBufs] = {};
     bool stageReady = false;
+    // optional per-kernel timing (trq_profile_enable): events around the trace and resolve kernels
+    bool profile = false;
+    cudaEvent_t evProf[kProfRing][3] = {};
+    uint32_t profHead = 0, profCount = 0;
 };
 
 namespace {
@@ -93,6 +98,8 @@ void free_scene(trq_scene* s) {
         if (s->evCompute[b]) cudaEventDestroy(s->evCompute[b]);
         if (s->evD2H[b]) cudaEventDestroy(s->evD2H[b]);
     }
+    for (int k = 0; k < kProfRing; ++k)
+        for (int j = 0; j < 3; ++j) if (s->evProf[k][j]) cudaEventDestroy(s->evProf[k][j]);
     if (s->sH2D) cudaStreamDestroy(s->sH2D);
     if (s->sCompute) cudaStreamDestroy(s->sCompute);
     if (s->sD2H) cudaStreamDestroy(s->sD2H);
@@ -170,20 +177,31 @@ int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_i
 int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, trq_hit* d_hits, cudaStream_t st) {
     if (n == 0) return TRQ_OK;
     const bool any = (flags & TRQ_TRACE_ANY) != 0;
+    cudaEvent_t* prof = nullptr;
+    if (s->profile) {
+        prof = s->evProf[s->profHead % kProfRing];
+        s->profHead++; if (s->profCount < kProfRing) s->profCount++;
+    }
     if (flags & TRQ_KERNEL_REFLAYOUT) {
         const unsigned block = 128;
         const uint64_t grid = (n + block - 1) / block;
         if (grid > 0x7fffffffull) return trq::fail(TRQ_ERR_INVALID, "trq_trace: batch too large");
+        if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));
         if (any) trace_reflayout_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
         else     trace_reflayout_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
         g_launches++;
     } else {
         static const uint32_t refillMin = [] {
             const char* e = getenv("TRQ_REFILL_MIN");
+            int v = e ? atoi(e) : 12;      // B200 sweep (profiles/): 8..16 is flat within 3% on C3 and the 1M soup
+            return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
+        }();
+        static const uint32_t leafBatch = [] {
+            const char* e = getenv("TRQ_LEAF_BATCH");
             int v = e ? atoi(e) : 8;
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
-        static const int blocksPerSMOverride = [] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
+        static const int blocksPerSMOverride =[] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
         const size_t smem = (size_t)s->stackDepth * TRQ_BLOCK * sizeof(uint32_t);
         int perSM = 0;
         if (any) TRQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, trace_packed_kernel<true>, TRQ_BLOCK, smem));
@@ -197,17 +215,20 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         TRQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         TraceParams P;
         P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
-        P.stackDepth = s->stackDepth; P.refillMin = refillMin;
+        P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
+        if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));
         if (any) trace_packed_kernel<true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
         else     trace_packed_kernel<false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
         g_launches++;
     }
+    if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
     {
         const unsigned block = 256;
         const uint64_t grid = (n + block - 1) / block;
         resolve_hits_kernel<<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
         g_launches++;
     }
+    if (prof) TRQ_CUDA(cudaEventRecord(prof[2], st));
     TRQ_CUDA(cudaGetLastError());
     return TRQ_OK;
 }
@@ -373,6 +394,34 @@ int trq_scene_destroy(trq_scene* s) {
 int trq_scene_info(const trq_scene* s, trq_scene_info_t* info) {
     if (!s || !info) return trq::fail(TRQ_ERR_INVALID, "trq_scene_info: NULL argument");
     *info = s->info;
+    return TRQ_OK;
+}
+
+int trq_profile_enable(trq_scene* s, int on) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_profile_enable: NULL scene");
+    DeviceGuard guard(s->device);
+    if (on && !s->evProf[0][0]) {
+        for (int k = 0; k < kProfRing; ++k)
+            for (int j = 0; j < 3; ++j) TRQ_CUDA(cudaEventCreate(&s->evProf[k][j]));
+    }
+    s->profile = on != 0;
+    s->profHead = 0; s->profCount = 0;
+    return TRQ_OK;
+}
+
+int trq_profile_read(trq_scene* s, uint32_t* nLaunches, float* traceMs, float* resolveMs) {
+    if (!s || !nLaunches || !traceMs || !resolveMs) return trq::fail(TRQ_ERR_INVALID, "trq_profile_read: NULL argument");
+    DeviceGuard guard(s->device);
+    *nLaunches = 0; *traceMs = 0.0f; *resolveMs = 0.0f;
+    for (uint32_t k = 0; k < s->profCount; ++k) {
+        cudaEvent_t* ev = s->evProf[(s->profHead - 1 - k) % kProfRing];
+        TRQ_CUDA(cudaEventSynchronize(ev[2]));
+        float a = 0.0f, b = 0.0f;
+        TRQ_CUDA(cudaEventElapsedTime(&a, ev[0], ev[1]));
+        TRQ_CUDA(cudaEventElapsedTime(&b, ev[1], ev[2]));
+        *traceMs += a; *resolveMs += b; (*nLaunches)++;
+    }
+    s->profHead = 0; s->profCount = 0;
     return TRQ_OK;
 }
 

@@ -1,0 +1,137 @@
+"""Multi-GPU plumbing for the ray query: one process per GPU over torch.distributed.
+
+The path shards by ray batch: the scene is read-only and replicated, rays are
+independent, so there is NO collective on the data path. The only communication is
+  * once per scene: broadcast of the six reference-layout arrays from rank 0 (NCCL over NVLink when the
+    backend is nccl; gloo on CPU for the tests), after which every rank calls trq_scene_create;
+  * optionally, after tracing: all-gather of the 32-byte hit records for a consumer that wants them whole.
+"""
+import os
+
+import numpy as np
+
+from . import layout as L
+from .scene import Primitive
+
+_FIELDS = (("sphereList", L.sphere_dtype), ("squareList", L.square_dtype), ("cubeList", L.cube_dtype),
+           ("triList", L.vertex_dtype), ("idxList", np.dtype("<u4")), ("bvhList", L.bvh_dtype))
+
+
+def env_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init(backend=None):
+    """Initialise the default process group from the torchrun environment (no-op for world size 1)."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = env_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def shard_range(n, rank, world):
+    """Contiguous ray range [r*N/R, (r+1)*N/R) of rank r."""
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def _comm_device():
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def replicate_primitive(prim, src=0):
+    """Broadcast the six reference-layout arrays from rank `src`; returns a Primitive on every rank.
+    `prim` is only read on the source rank (pass None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return prim
+    dev = _comm_device()
+    rank = dist.get_rank()
+    sizes = torch.zeros(len(_FIELDS), dtype=torch.int64, device=dev)
+    if rank == src:
+        sizes = torch.tensor([getattr(prim, k).nbytes for k, _ in _FIELDS], dtype=torch.int64, device=dev)
+    dist.broadcast(sizes, src)
+    out = {}
+    for (k, dt), nbytes in zip(_FIELDS, sizes.tolist()):
+        if nbytes == 0:
+            out[k] = np.zeros(0, dtype=dt)
+            continue
+        if rank == src:
+            buf = torch.from_numpy(getattr(prim, k).view(np.uint8).reshape(-1)).to(dev)
+        else:
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        dist.broadcast(buf, src)
+        out[k] = getattr(prim, k) if rank == src else buf.cpu().numpy().view(dt).reshape(-1).copy()
+    return Primitive(**out)
+
+
+def checksum_primitive(prim):
+    """Order-sensitive 64-bit checksum of the scene bytes (to verify the broadcast)."""
+    h = np.uint64(1469598103934665603)
+    for k, _ in _FIELDS:
+        a = getattr(prim, k).view(np.uint8).reshape(-1)
+        pad = (-a.size) % 8
+        w = np.concatenate([a, np.zeros(pad, dtype=np.uint8)]).view(np.uint64)
+        with np.errstate(over="ignore"):
+            h = h ^ (np.bitwise_xor.reduce(w * (np.arange(w.size, dtype=np.uint64) * np.uint64(2) + np.uint64(1))) if w.size else np.uint64(0))
+            h = h * np.uint64(1099511628211)
+    return int(h)
+
+
+def gather_hits(hits):
+    """All-gather per-rank hit tensors ((n_r, 8) float32, possibly different n_r) -> list of tensors, rank order."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [hits]
+    world = dist.get_world_size()
+    dev = hits.device
+    n = torch.tensor([hits.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    m = max(ns)
+    padded = torch.zeros((m, 8), dtype=torch.float32, device=dev)
+    padded[: hits.shape[0]] = hits
+    outs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(outs, padded)
+    return [o[:k] for o, k in zip(outs, ns)]
+
+
+def max_over_ranks(value):
+    """MAX all-reduce of a python float (device timing rule: multi-GPU time = max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_comm_device())
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value):
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=_comm_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()

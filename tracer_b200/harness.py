@@ -303,19 +303,29 @@ def scene_reference_cornell(with_spheres=True):
 
 def scene_c1(seed=42, seq=54):
     """C1: RT_Nextweek randomScene (Render.swift:83-130) as Sphere leaves in the RT_Metal SAH BVH."""
-    xi = pcg32_floats(seed, seq, 3 * 22 * 22)
+    u32 = np.empty(12 * 21 * 21, dtype=np.uint32)
+    lib.trqh_pcg32_fill_u32(seed, seq, u32.size, u32.ctypes.data)
+    xi = u32.astype(np.float32) / f32(0xFFFFFFFF)               # randomFloat()  Random.swift:3-6 (arc4random -> PCG32)
     k = 0
-    sph = [make_sphere(1000, (0, -1000, 0), 0)]
-    for a in range(-11, 11):
-        for b in range(-11, 11):
-            k += 1                                              # choose_mat draw
-            cx = f32(a) + f32(0.9) * xi[k]; k += 1
-            cz = f32(b) + f32(0.9) * xi[k]; k += 1
-            c = np.array([cx, 0.2, cz], dtype=np.float32)
+
+    def draw():
+        nonlocal k
+        k += 1
+        return xi[k - 1]
+
+    sph = [make_sphere(1000, (0, -1000, 0), 0), make_sphere(1.0, (0, 1, 0), 2),
+           make_sphere(1.0, (-4, 1, 0), 3), make_sphere(1.0, (4, 1, 0), 4)]
+    for a in range(-10, 11):
+        for b in range(-10, 11):
+            mat = draw()
+            c = np.array([f32(a) + f32(0.9) * draw(), 0.2, f32(b) + f32(0.9) * draw()], dtype=np.float32)
             if np.linalg.norm(c - np.array([4, 0.2, 0], dtype=np.float32)) > 0.9:
+                # material draws consumed by the reference (MovingSphere frozen at centerS, t = 0)
+                k += 7 if mat < 0.8 else (4 if mat < 0.95 else 0)
                 sph.append(make_sphere(0.2, c, 1))
-    sph += [make_sphere(1.0, (0, 1, 0), 2), make_sphere(1.0, (-4, 1, 0), 3), make_sphere(1.0, (4, 1, 0), 4)]
     spheres = np.array(sph, dtype=L.sphere_dtype)
+    # RT_Nextweek spheres have no +0.0001 radius pad (Sphere.swift): undo MakeSphere's
+    spheres["radius"] = np.where(np.arange(len(sph)) == 0, f32(1000), np.where(np.arange(len(sph)) < 4, f32(1.0), f32(0.2)))
     return build_primitive(spheres=spheres)
 
 

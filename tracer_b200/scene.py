@@ -145,6 +145,15 @@ class Scene:
         flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS
         check(lib.trq_trace(self._h, rays_ptr, n, flags, hits_ptr, None), "trq_trace")
 
+    def profile(self, on=True):
+        check(lib.trq_profile_enable(self._h, 1 if on else 0), "trq_profile_enable")
+
+    def profile_read(self):
+        """-> (launches, trace_kernel_ms_sum, resolve_kernel_ms_sum) since the last read."""
+        n, a, b = C.c_uint32(0), C.c_float(0), C.c_float(0)
+        check(lib.trq_profile_read(self._h, C.byref(n), C.byref(a), C.byref(b)), "trq_profile_read")
+        return n.value, a.value, b.value
+
     def expand(self, rays, hits, out=None, stream=None):
         """trq_expand_hits: HitRecord fields (p, gn, sn, uv, f, material) for the hits of `rays`."""
         if isinstance(rays, np.ndarray):
