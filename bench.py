@@ -112,7 +112,10 @@ def make_rays_cpu_sample(name, prim, ref_trace_records, stride):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 20 ms from before the warm-up until after the timed region; samples are kept when
+    their timestamp falls inside [mark_start, mark_end] (the timed region), widened to the whole loaded span
+    (warm-up + timed) when the timed region is too short to catch any."""
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -120,42 +123,54 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
+        self.t_load = time.time()
         self.t0 = self.t1 = None
 
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "window": None}
         if self.proc is None:
             return out
-        time.sleep(0.06)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
                 if len(p) < 9:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(p[1]), float(p[2]), [v.lower().startswith("active") for v in p[5:9]]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except OSError:
             pass
-        if sm:
-            # "under load": the upper half of the samples (the sampler also sees idle time around the region)
-            load = sorted(sm)[len(sm) // 2:]
-            out.update({"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)})
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for window, lo, hi in (("timed region", self.t0, self.t1), ("warm-up + timed region", self.t_load, self.t1)):
+            if lo is None or hi is None:
+                continue
+            sel = [r for r in rows if lo - 0.02 <= r[0] <= hi + 0.02]
+            if sel:
+                reasons = sorted({n for r in sel for n, on in zip(names, r[3]) if on})
+                out.update({"sm_mhz": float(np.median([r[1] for r in sel])), "sm_max_mhz": max(r[2] for r in sel),
+                            "reasons": reasons, "samples": len(sel), "window": window})
+                break
         return out
 
 
@@ -272,15 +287,16 @@ def run_gpu_arm(a):
     def step():
         scene.hit(d_rays, any=any_hit, out=d_hits)
 
+    sampler = ClockSampler(local_rank)                  # runs from before the warm-up to the end of the timed region
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
 
     # ---- timed region: K steps, device events, barrier + synchronize on both sides
     scene.profile(True)
-    sampler = ClockSampler(local_rank)
     launches0 = launch_count()
     D.barrier(); torch.cuda.synchronize()
+    sampler.mark_start()
     total_ms = 0.0
     if flush is None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -299,6 +315,7 @@ def run_gpu_arm(a):
             evs.append((e0, e1))
         torch.cuda.synchronize()
         total_ms = sum(x.elapsed_time(y) for x, y in evs)
+    sampler.mark_end()
     D.barrier()
     launches = launch_count() - launches0
     clocks = sampler.stop()
@@ -335,6 +352,8 @@ def run_gpu_arm(a):
         gathered = int(sum(p.shape[0] for p in parts))
 
     if rank != 0:
+        D.barrier()
+        _shutdown()
         return 0
 
     # ---- CPU baseline + algorithmic bytes (rank 0, N=1 only for the baseline)
@@ -381,19 +400,28 @@ def run_gpu_arm(a):
         }),
         "roofline": {"bound": "hbm", "kernel": "trace_packed_kernel", "achieved": None if achieved is None else round(achieved, 1),
                      "peak": peak, "unit": "GB/s", "frac": None if achieved is None else round(achieved / peak, 4),
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_ray": round(bpr, 1),
+                     "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write)",
+                     "algorithmic_gb_per_launch": round(bpr * n / 1e9, 3), "peak_source": peak_src, "algorithmic_bytes_per_ray": round(bpr, 1),
                      "kernel_ms": round(trace_ms_avg, 4), "resolve_kernel_ms": round(resolve_ms / max(1, nl), 4),
                      "kernel_share_of_step": round(trace_ms_avg / max(1e-9, total_ms / a.steps), 4)},
         "cpu_baseline": cpu,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 32),
                 "steps": e2e_steps, "host_path_equals_device_path": same, "timing": "wall clock around K synchronous C-ABI calls, max over ranks"},
         "gpu_launches": int(launches),
-        "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
+        "clocks": clocks,
     }
     if gathered is not None:
         line["gathered_hits_checked"] = gathered
     print(json.dumps(line), flush=True)
+    D.barrier()
+    _shutdown()
     return 0
+
+
+def _shutdown():
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def main():

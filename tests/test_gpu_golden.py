@@ -1,0 +1,101 @@
+"""GPU: the CUDA path (through the C-ABI) against the golden vectors produced by the reference's own headers
+(tests/golden/rq_golden.npz), and size-independent properties at BASELINE's full C3 size."""
+import numpy as np
+import pytest
+
+from tracer_b200 import layout as L
+
+from .util import CASES, assert_records_match_reference, bits, golden_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.mark.parametrize("reflayout", [False, True])
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_matches_reference_golden(built, name, reflayout):
+    torch = _torch()
+    from tracer_b200 import Scene, hits_to_numpy, rays_to_torch
+    prim, rays, any_hit, want = golden_case(name)
+    scene = Scene(prim, 0)
+    d = rays_to_torch(rays, "cuda:0")
+    h = scene.hit(d, any=any_hit, reflayout=reflayout)
+    hits = hits_to_numpy(h)
+    hit = (hits["flags"] & 1) == 1
+    assert np.array_equal(hit, want["hit"] == 1), "miss flags must be bit-exact"
+    assert np.array_equal(bits(hits["t"][hit]), bits(want["t"][hit]))
+    assert np.array_equal(hits["material"][hit], want["material"][hit])
+    assert np.array_equal(((hits["flags"] >> 1) & 1)[hit], want["front"][hit])
+    recs = scene.expand(d, h).cpu().numpy().view(L.record_dtype).reshape(-1)
+    assert_records_match_reference(recs, want, hits=hits, sphere_uv_atol=1e-5, where=name)
+    scene.close()
+
+
+@pytest.fixture(scope="module")
+def c3(built):
+    _torch()
+    from tracer_b200 import Scene, harness as H, rays_to_torch
+    prim = H.scene_c3(2)
+    scene = Scene(prim, 0)
+    primary = H.cornell_camera_rays(3840, 2160)
+    d = rays_to_torch(primary, "cuda:0")
+    recs = scene.expand(d, scene.hit(d)).cpu().numpy().view(L.record_dtype).reshape(-1)
+    bounce, _ = H.bounce_rays(recs)
+    return prim, scene, bounce
+
+
+def test_c3_full_size_properties(c3, port):
+    """BASELINE C3 at full size (1.0 M triangles, ~6.2 M incoherent bounce rays)."""
+    torch = _torch()
+    from tracer_b200 import hits_to_numpy, rays_to_torch
+    prim, scene, rays = c3
+    assert prim.nTri > 1_000_000 and rays.size > 6_000_000
+    d = rays_to_torch(rays, "cuda:0")
+    a = scene.hit(d)
+    b = scene.hit(d)
+    assert torch.equal(a, b), "not idempotent"
+    r = scene.hit(d, reflayout=True)
+    assert torch.equal(a, r), "packed kernel and reference-layout transcription disagree"
+    anyh = scene.hit(d, any=True)
+    ai, ci = anyh.view(torch.int32), a.view(torch.int32)
+    assert torch.equal(ai[:, 7] & 1, ci[:, 7] & 1), "any-hit flag != closest-hit flag at tmax = FLT_MAX"
+    hit = (ci[:, 7] & 1) == 1
+    assert bool((anyh[hit, 0] >= a[hit, 0]).all()), "an any-hit t is closer than the closest hit"
+    # sharding: tracing the two halves separately gives the same bytes as the whole batch
+    half = rays.size // 2
+    parts = torch.cat([scene.hit(d[:half].contiguous()), scene.hit(d[half:].contiguous())])
+    assert torch.equal(parts, a)
+    # host-pointer path (chunked, three streams) == device path
+    host = scene.hit(rays)
+    assert np.array_equal(host.view(np.uint8), hits_to_numpy(a).view(np.uint8))
+    # oracle on a strided 1% sample: ids and t bit-exact
+    sub = np.ascontiguousarray(rays[::97])
+    want = port.trace(prim, sub, nthreads=8)["hits"]
+    got = hits_to_numpy(a)[::97]
+    for k in ("flags", "pType", "pIndex", "leafNode", "material"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("t", "u", "v"):
+        assert np.array_equal(bits(got[k]), bits(want[k])), k
+
+
+def test_streams_are_reentrant(c3):
+    torch = _torch()
+    from tracer_b200 import rays_to_torch
+    prim, scene, rays = c3
+    d = rays_to_torch(rays[:1_000_000], "cuda:0")
+    ref = scene.hit(d)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs = []
+    for s in (s1, s2, s1, s2):
+        with torch.cuda.stream(s):
+            outs.append(scene.hit(d))
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o, ref)

@@ -44,9 +44,9 @@ __device__ __forceinline__ bool box_hit_t(const f3& mini, const f3& maxi, const 
 // hit_t specialised for Scene::hit's range_t.x == FLT_MIN (Render.hh:143), same results with fewer
 // instructions: after `tmin = max(tmin, FLT_MIN)` tmin is >= FLT_MIN > 0 for every input (fmaxf drops
 // NaNs), so `tmax < 0` implies `tmax < tmin` and the `tmin < 0 ? tmax : tmin` select always takes tmin.
-__device__ __forceinline__ bool box_entry(const f3& mini, const f3& maxi, const RayCtx& r, float range_y, float& t) {
-    f3 ts = mul3(sub3(mini, r.o), r.inv);
-    f3 te = mul3(sub3(maxi, r.o), r.inv);
+__device__ __forceinline__ bool box_entry(const f3& mini, const f3& maxi, const f3& o, const f3& inv, float range_y, float& t) {
+    f3 ts = mul3(sub3(mini, o), inv);
+    f3 te = mul3(sub3(maxi, o), inv);
     float tmin = fmaxf(fmaxf(fminf(ts.x, te.x), fminf(ts.y, te.y)), fminf(ts.z, te.z));
     float tmax = fminf(fminf(fmaxf(ts.x, te.x), fmaxf(ts.y, te.y)), fmaxf(ts.z, te.z));
     tmin = fmaxf(tmin, FLT_MIN);
@@ -146,7 +146,7 @@ __device__ __forceinline__ void sphere_surface(const RefSphere* __restrict__ sp,
 }
 
 // Square::hit_test  (Square.hh:82-111)
-__device__ __noinline__ bool square_hit(const RefSquare* __restrict__ sq, const RayCtx& r,
+__device__ __forceinline__ bool square_hit(const RefSquare* __restrict__ sq, const RayCtx& r,
                                         float range_x, float range_y, float& t, Surface* s) {
     unsigned ai = sq->axis_i, aj = sq->axis_j, ak = sq->axis_k;
     float tt = fdiv(fsub(sq->value_k, get3(r.o, ak)), get3(r.d, ak));
@@ -231,7 +231,7 @@ __device__ __forceinline__ bool box_hit_record(const RefAABB& b, const f3& o, co
 }
 
 // Cube::hit_test  (Cube.hh:17-47)
-__device__ __noinline__ bool cube_hit(const RefCube* __restrict__ cb, const RayCtx& r,
+__device__ __forceinline__ bool cube_hit(const RefCube* __restrict__ cb, const RayCtx& r,
                                       float range_x, float range_y, float& t, Surface* s) {
     (void)range_x;
     f3 lo = m4_mul3(cb->inverse, r.o, 1.0f);

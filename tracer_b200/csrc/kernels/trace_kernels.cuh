@@ -47,16 +47,24 @@ __device__ __forceinline__ void store_compact(trq_hit* hits, uint64_t i, bool hi
     out[0] = a; out[1] = b;
 }
 
-// Leaf tests that read reference-layout structs (rare leaf types). Returns true on accept.
-__device__ __forceinline__ bool leaf_square_cube(const SceneDev& S, uint32_t kind, uint32_t leafNode, const RayCtx& ray,
-                                                 float range_y, float& t, float& u, float& v, uint32_t& aux) {
-    const uint32_t pIndex = S.bvh[leafNode].pIndex;
+// Leaf tests that read reference-layout structs (rare leaf types: Square, Cube). Out of line and fed with
+// scalars by value so that the hot loops keep the ray in registers (no local-memory RayCtx); the ray context is
+// rebuilt here (1/d recomputed: same bits). out = {t, u, v, bits(aux)}. Returns true on accept.
+__device__ __noinline__ bool leaf_square_cube(const RefBVH* __restrict__ bvh, const RefSquare* __restrict__ squares,
+                                              const RefCube* __restrict__ cubes, uint32_t kind, uint32_t leafNode,
+                                              float ox, float oy, float oz, float dx, float dy, float dz,
+                                              float range_y, float4* out) {
+    const RayCtx ray = make_ray_ctx(ox, oy, oz, dx, dy, dz);
+    const uint32_t pIndex = bvh[leafNode].pIndex;
+    float t = 0.0f;
     if (kind == REF_SQUARE) {
-        return square_hit(&S.squares[pIndex], ray, FLT_MIN, range_y, t, nullptr);
+        if (!square_hit(&squares[pIndex], ray, FLT_MIN, range_y, t, nullptr)) return false;
+        *out = make_float4(t, 0.0f, 0.0f, 0.0f);
+        return true;
     }
     Surface s;
-    if (!cube_hit(&S.cubes[pIndex], ray, FLT_MIN, range_y, t, &s)) return false;
-    u = s.uvx; v = s.uvy; aux = s.front | (s.material << 1);
+    if (!cube_hit(&cubes[pIndex], ray, FLT_MIN, range_y, t, &s)) return false;
+    *out = make_float4(t, s.uvx, s.uvy, __uint_as_float(s.front | (s.material << 1)));
     return true;
 }
 
@@ -109,7 +117,10 @@ trace_reflayout_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* __
             } else if (pType == TRQ_SPHERE) {                             // :221-223
                 h = sphere_hit(ld3(S.spheres[pIndex].center), S.spheres[pIndex].radius, ray, FLT_MIN, range_y, t);
             } else if (pType == TRQ_SQUARE || pType == TRQ_CUBE) {        // :224-229
-                h = leaf_square_cube(S, pType == TRQ_SQUARE ? REF_SQUARE : REF_CUBE, sel, ray, range_y, t, u, v, a);
+                float4 o4;
+                h = leaf_square_cube(S.bvh, S.squares, S.cubes, pType == TRQ_SQUARE ? REF_SQUARE : REF_CUBE, sel,
+                                     ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, range_y, &o4);
+                if (h) { t = o4.x; u = o4.y; v = o4.z; a = __float_as_uint(o4.w); }
             }
             if (h) { range_y = t; best = sel; bu = u; bv = v; aux = a; }
             if (ANY && range_y < test_t) { done_any = true; break; }      // :244
@@ -136,20 +147,39 @@ struct TraceParams {
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
 };
 
+// Per-ray state that the interior loop never touches is parked in shared memory ([word][TRQ_BLOCK],
+// lane-major => bank-conflict free) so that the hot loop fits in 48 registers (5 resident CTAs per SM).
+enum : uint32_t { COLD_TEST_T = 0, COLD_BEST, COLD_U, COLD_V, COLD_AUX, COLD_RAY, COLD_DX, COLD_DY, COLD_DZ, COLD_WORDS };
+
+#ifndef TRQ_MIN_BLOCKS
+#define TRQ_MIN_BLOCKS 5
+#endif
+
 template <bool ANY>
-__global__ void __launch_bounds__(TRQ_BLOCK)
+__global__ void __launch_bounds__(TRQ_BLOCK, TRQ_MIN_BLOCKS)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
-    extern __shared__ uint32_t smem_stack[];                 // [stackDepth][TRQ_BLOCK]: lane-major => conflict-free
-    uint32_t* const stk = smem_stack + threadIdx.x;
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t* const stk = smem_u32 + threadIdx.x;                                   // [stackDepth][TRQ_BLOCK]
+    uint32_t* const cold = smem_u32 + P.stackDepth * TRQ_BLOCK + threadIdx.x;        // [COLD_WORDS][TRQ_BLOCK]
+    float* const coldf = reinterpret_cast<float*>(cold);
     const unsigned lane = threadIdx.x & 31u;
-    const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
-    const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
 
     bool active = false, exhausted = false;
-    uint64_t rayIdx = 0;
-    RayCtx ray; ray.o = ray.d = ray.inv = make_f3(0.f, 0.f, 0.f);
-    float test_t = 0.0f, range_y = 0.0f, bu = 0.0f, bv = 0.0f;
-    uint32_t cur = TRQ_REF_DONE_WORD, sp = 0, best = 0xffffffffu, aux = 0;
+    f3 ro = make_f3(0.f, 0.f, 0.f), rinv = make_f3(0.f, 0.f, 0.f);
+    float range_y = 0.0f;
+    uint32_t cur = TRQ_REF_DONE_WORD, sp = 0;
+
+    // ray finished: write the compact result (resolved into trq_hit by resolve_hits_kernel)
+    auto finish = [&]() {
+        const uint32_t best = cold[COLD_BEST * TRQ_BLOCK];
+        const bool hit = (range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) && best != 0xffffffffu;   // Render.hh:251
+        store_compact(P.hits, cold[COLD_RAY * TRQ_BLOCK], hit, range_y, best,
+                      coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK]);
+        active = false;
+    };
+    auto pop = [&]() {
+        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * TRQ_BLOCK]; }
+    };
 
     for (;;) {
         // ---- refill idle lanes from the global queue: one atomic per warp ----
@@ -163,13 +193,21 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             if (!active) {
                 const uint64_t idx = base + (uint64_t)__popc(idleMask & ((1u << lane) - 1u));
                 if (idx < P.n) {
-                    rayIdx = idx;
                     const float4 r0 = ldg4(reinterpret_cast<const float4*>(P.rays + idx));
                     const float4 r1 = ldg4(reinterpret_cast<const float4*>(P.rays + idx) + 1);
-                    ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
-                    test_t = r0.w; range_y = r0.w;                        // Render.hh:143
-                    best = 0xffffffffu; bu = bv = 0.0f; aux = 0; sp = 0;
+                    const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                    ro = ray.o; rinv = ray.inv;
+                    range_y = r0.w;                                        // Render.hh:143  range_t = (FLT_MIN, test_t)
+                    sp = 0;
+                    const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
+                    const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
                     if (box_hit(rootMin, rootMax, ray, FLT_MIN, range_y)) {            // :145
+                        coldf[COLD_TEST_T * TRQ_BLOCK] = r0.w;
+                        cold[COLD_BEST * TRQ_BLOCK] = 0xffffffffu;
+                        coldf[COLD_U * TRQ_BLOCK] = 0.0f; coldf[COLD_V * TRQ_BLOCK] = 0.0f;
+                        cold[COLD_AUX * TRQ_BLOCK] = 0u;
+                        cold[COLD_RAY * TRQ_BLOCK] = (uint32_t)idx;
+                        coldf[COLD_DX * TRQ_BLOCK] = r1.x; coldf[COLD_DY * TRQ_BLOCK] = r1.y; coldf[COLD_DZ * TRQ_BLOCK] = r1.z;
                         cur = S.rootRef; active = true;
                     } else {
                         store_compact(P.hits, idx, false, 0.0f, 0u, 0.0f, 0.0f, 0u);
@@ -199,52 +237,51 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     ldg8(np, q0, q1);
                     ldg8(np + 2, q2, q3);
                     float tl = range_y, tr = range_y;                     // :157
-                    const bool lt = box_entry(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ray, range_y, tl);   // :159
-                    const bool rt = box_entry(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ray, range_y, tr);   // :160
+                    const bool lt = box_entry(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ro, rinv, range_y, tl);   // :159
+                    const bool rt = box_entry(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ro, rinv, range_y, tr);   // :160
                     const uint32_t lref = __float_as_uint(q0.w), rref = __float_as_uint(q1.w);
                     if (!lt && !rt) {                                     // :162-169  pop
-                        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * TRQ_BLOCK]; }
+                        pop();
                     } else {
                         const bool selLeft = tl < tr;                     // :174 (ties -> right, quirk included)
                         if (lt && rt) { stk[sp * TRQ_BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
                         cur = selLeft ? lref : rref;
                     }
-                    if (cur == TRQ_REF_DONE_WORD) {
-                        const bool hit = (range_y < test_t) && best != 0xffffffffu;   // :251
-                        store_compact(P.hits, rayIdx, hit, range_y, best, bu, bv, aux);
-                        active = false;
-                    }
+                    if (cur == TRQ_REF_DONE_WORD) finish();
                 }
             }
-            if (active) {
+            if (active && TRQ_REF_KIND(cur) != REF_INTERIOR) {
                 const uint32_t kind = TRQ_REF_KIND(cur);
-                if (kind != REF_INTERIOR) {
-                    bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t leaf = 0, a = 0;
-                    if (kind == REF_TRI) {
-                        const float4* tp = S.tris + (size_t)TRQ_REF_INDEX(cur) * 3u;
-                        const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
-                        leaf = __float_as_uint(t0.w);
-                        h = tri_hit(make_f3(t0.x, t0.y, t0.z), make_f3(t1.x, t1.y, t1.z), make_f3(t2.x, t2.y, t2.z),
-                                    ray, FLT_MIN, range_y, t, u, v);
-                    } else if (kind == REF_SPHERE) {
-                        const float4* spp = S.sph + (size_t)TRQ_REF_INDEX(cur) * 2u;
-                        const float4 s0 = ldg4(spp), s1 = ldg4(spp + 1);
-                        leaf = __float_as_uint(s1.x);
-                        h = sphere_hit(make_f3(s0.x, s0.y, s0.z), s0.w, ray, FLT_MIN, range_y, t);
-                    } else if (kind == REF_SQUARE || kind == REF_CUBE) {
-                        leaf = TRQ_REF_INDEX(cur);
-                        h = leaf_square_cube(S, kind, leaf, ray, range_y, t, u, v, a);
-                    }
-                    if (h) { range_y = t; best = leaf; bu = u; bv = v; aux = a; }
-                    if (ANY && range_y < test_t) cur = TRQ_REF_DONE_WORD; // :244
-                    else if (sp == 0) cur = TRQ_REF_DONE_WORD;
-                    else { --sp; cur = stk[sp * TRQ_BLOCK]; }
+                RayCtx ray;
+                ray.o = ro; ray.inv = rinv;
+                ray.d = make_f3(coldf[COLD_DX * TRQ_BLOCK], coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
+                bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t leaf = 0, a = 0;
+                if (kind == REF_TRI) {
+                    const float4* tp = S.tris + (size_t)TRQ_REF_INDEX(cur) * 3u;
+                    const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
+                    leaf = __float_as_uint(t0.w);
+                    h = tri_hit(make_f3(t0.x, t0.y, t0.z), make_f3(t1.x, t1.y, t1.z), make_f3(t2.x, t2.y, t2.z),
+                                ray, FLT_MIN, range_y, t, u, v);
+                } else if (kind == REF_SPHERE) {
+                    const float4* spp = S.sph + (size_t)TRQ_REF_INDEX(cur) * 2u;
+                    const float4 s0 = ldg4(spp), s1 = ldg4(spp + 1);
+                    leaf = __float_as_uint(s1.x);
+                    h = sphere_hit(make_f3(s0.x, s0.y, s0.z), s0.w, ray, FLT_MIN, range_y, t);
+                } else if (kind == REF_SQUARE || kind == REF_CUBE) {
+                    leaf = TRQ_REF_INDEX(cur);
+                    float4 o4;
+                    h = leaf_square_cube(S.bvh, S.squares, S.cubes, kind, leaf, ro.x, ro.y, ro.z, ray.d.x, ray.d.y, ray.d.z, range_y, &o4);
+                    if (h) { t = o4.x; u = o4.y; v = o4.z; a = __float_as_uint(o4.w); }
                 }
-                if (cur == TRQ_REF_DONE_WORD) {
-                    const bool hit = (range_y < test_t) && best != 0xffffffffu;       // :251
-                    store_compact(P.hits, rayIdx, hit, range_y, best, bu, bv, aux);
-                    active = false;
+                if (h) {
+                    range_y = t;
+                    cold[COLD_BEST * TRQ_BLOCK] = leaf;
+                    coldf[COLD_U * TRQ_BLOCK] = u; coldf[COLD_V * TRQ_BLOCK] = v;
+                    cold[COLD_AUX * TRQ_BLOCK] = a;
                 }
+                if (ANY && range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) cur = TRQ_REF_DONE_WORD;   // :244
+                else pop();
+                if (cur == TRQ_REF_DONE_WORD) finish();
             }
         } while (__popc(__ballot_sync(0xffffffffu, active)) > keepGoing);
     }

@@ -176,6 +176,15 @@ int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_i
 
 int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, trq_hit* d_hits, cudaStream_t st) {
     if (n == 0) return TRQ_OK;
+    constexpr uint64_t kMaxPerLaunch = 1ull << 31;             // the kernels keep a 32-bit ray index per lane
+    if (n > kMaxPerLaunch) {
+        for (uint64_t off = 0; off < n; off += kMaxPerLaunch) {
+            const uint64_t m = (n - off) < kMaxPerLaunch ? (n - off) : kMaxPerLaunch;
+            int rc = launch_trace(s, d_rays + off, m, flags, d_hits + off, st);
+            if (rc != TRQ_OK) return rc;
+        }
+        return TRQ_OK;
+    }
     const bool any = (flags & TRQ_TRACE_ANY) != 0;
     cudaEvent_t* prof = nullptr;
     if (s->profile) {
@@ -202,7 +211,11 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
         static const int blocksPerSMOverride =[] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
-        const size_t smem = (size_t)s->stackDepth * TRQ_BLOCK * sizeof(uint32_t);
+        const size_t smem = ((size_t)s->stackDepth + COLD_WORDS) * TRQ_BLOCK * sizeof(uint32_t);
+        if (smem > 48 * 1024) {
+            TRQ_CUDA(cudaFuncSetAttribute(trace_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            TRQ_CUDA(cudaFuncSetAttribute(trace_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         int perSM = 0;
         if (any) TRQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, trace_packed_kernel<true>, TRQ_BLOCK, smem));
         else     TRQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, trace_packed_kernel<false>, TRQ_BLOCK, smem));

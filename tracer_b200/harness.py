@@ -275,7 +275,8 @@ def scene_c4(levels=2, n_random=10000, seed=7):
         c = (f32(-245) + f32(1045) * xi[k, 0], f32(555) * xi[k, 1], f32(555) * xi[k, 2])
         sph.append(make_sphere(f32(2) + f32(8) * xi[k, 3], c, 30))
     spheres = np.array(sph, dtype=L.sphere_dtype)
-    return build_primitive(tri, idx, spheres=spheres, squares=cornell_squares())  # squares kept for the light samples
+    # squareList is uploaded for the light samples (lights 5 / 6) but gets no leaves: the walls are triangles here
+    return build_primitive(tri, idx, spheres=spheres, squares=cornell_squares(), square_leaves=[])
 
 
 def scene_c4_lights(prim):
