@@ -42,10 +42,11 @@ WORKLOADS = {
     "c4": "C4: C3 geometry + 10,012 spheres, any-hit shadow rays toward light squares 5/6 from 3840x2160 primary hits",
     "c5": "C5: 10M-triangle random soup, 8M uniform incoherent rays per GPU",
     "soup1m": "1M-triangle random soup, 8M uniform incoherent rays",
+    "c1": "C1: RT_Nextweek randomScene (442 spheres) as Sphere leaves of the RT_Metal SAH BVH, 1280x720 primary rays (camera0)",
 }
 # algorithmic bytes per ray measured once by the instrumented oracle; used only if the
 # oracle cannot be run in this process. Recomputed live on the cpu_baseline sample otherwise.
-BYTES_PER_RAY_FALLBACK = {"c2": 1094.0, "c3": 1795.0, "c4": 1000.0, "c5": 8000.0, "soup1m": 7029.0}
+BYTES_PER_RAY_FALLBACK = {"c1": 700.0, "c2": 1094.0, "c3": 1778.0, "c4": 2887.0, "c5": 9184.0, "soup1m": 7039.0}
 
 
 def log(*a):
@@ -73,7 +74,15 @@ def build_scene(name):
         return H.scene_soup(10_000_000, seed=1, extent=0.004)
     if name == "soup1m":
         return H.scene_soup(1_000_000, seed=1, extent=0.01)
+    if name == "c1":
+        return H.scene_c1()
     raise SystemExit(f"unknown workload {name}")
+
+
+def c1_rays():
+    """RT_Nextweek camera0 (Render.swift:35-57): from (13,2,3) to the origin, vfov 20 deg, 1280x720."""
+    from tracer_b200 import harness as H
+    return H.camera_rays((13, 2, 3), (0, 0, 0), np.float32(20 * np.pi / 180), 1280, 720)
 
 
 def make_rays_gpu(name, prim, scene, rank, device):
@@ -82,6 +91,8 @@ def make_rays_gpu(name, prim, scene, rank, device):
     if name in ("c5", "soup1m"):
         n = 8_000_000
         return H.random_rays(n, seed=2, first=rank * n), False
+    if name == "c1":
+        return c1_rays(), False
     W, Hh = (1920, 1080) if name == "c2" else (3840, 2160)
     primary = H.cornell_camera_rays(W, Hh)
     d = rays_to_torch(primary, device)
@@ -101,6 +112,8 @@ def make_rays_cpu_sample(name, prim, ref_trace_records, stride):
     from tracer_b200 import harness as H
     if name in ("c5", "soup1m"):
         return H.random_rays(8_000_000 // stride, seed=2), False
+    if name == "c1":
+        return c1_rays(), False
     W, Hh = (1920, 1080) if name == "c2" else (3840, 2160)
     primary = H.cornell_camera_rays(W, Hh)[::stride].copy()
     recs = ref_trace_records(primary)
@@ -371,6 +384,17 @@ def run_gpu_arm(a):
             ids_ok = all(np.array_equal(got[k], want[k]) for k in ("flags", "pType", "pIndex", "leafNode"))
             t_ok = np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
             cpu["parity_on_sample"] = {"rays": int(chk.size), "ids_bit_exact": bool(ids_ok), "t_bit_exact": bool(t_ok)}
+            if a.workload == "c1":
+                # the config's NAMED baseline: RT_Nextweek's own CPU BVH (restated in C, oracle/nextweek_bvh.c)
+                from oracle.pyoracle import Nextweek
+                nw = Nextweek(prim.sphereList)
+                nw.trace(rays[:50000], nthreads=cores)
+                t0 = time.perf_counter(); ids, _ = nw.trace(rays, nthreads=cores); dt = time.perf_counter() - t0
+                mine = scene.hit(rays_to_torch(rays, device)).cpu().numpy().view(want.dtype).reshape(-1)
+                hit = (mine["flags"] & 1) == 1
+                cpu["nextweek_bvh"] = {"value": round(rays.size / dt / 1e6, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                                       "sample": f"all {rays.size} rays, {dt:.1f} s",
+                                       "same_sphere_as_gpu": round(float(np.mean(ids[hit] == mine["pIndex"][hit])), 6)}
         else:
             from oracle.pyoracle import Port
             pilot = rays[:: max(1, n // 40000)]

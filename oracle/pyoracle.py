@@ -210,3 +210,38 @@ class Reference:
         out = np.zeros(3, dtype=np.float32)
         self.lib.ref_cosine_sample_hemisphere(C.c_void_p(u.ctypes.data), C.c_void_p(out.ctypes.data))
         return out
+
+
+NEXTWEEK_PATH = os.path.join(_HERE, "libnextweek_bvh.so")
+
+
+class Nextweek:
+    """RT_Nextweek's CPU BVH (oracle/nextweek_bvh.c): config C1's named CPU baseline. Parity unpinned (no Swift)."""
+
+    def __init__(self, spheres, seed=42, seq=55):
+        if not os.path.exists(NEXTWEEK_PATH):
+            build(("port",))
+        self.lib = C.CDLL(NEXTWEEK_PATH)
+        self.lib.nw_build.restype = C.c_void_p
+        self.lib.nw_node_count.restype = C.c_uint32
+        cr = np.zeros((len(spheres), 4), dtype=np.float32)
+        cr[:, :3], cr[:, 3] = spheres["center"], spheres["radius"]
+        self.n = len(spheres)
+        self.h = C.c_void_p(self.lib.nw_build(C.c_void_p(cr.ctypes.data), C.c_uint32(self.n), C.c_uint64(seed), C.c_uint64(seq)))
+
+    def trace(self, rays, t_min=0.001, nthreads=1):
+        rays = np.ascontiguousarray(rays)
+        ids = np.zeros(rays.size, dtype=np.uint32)
+        t = np.zeros(rays.size, dtype=np.float32)
+        self.lib.nw_trace(self.h, C.c_void_p(rays.ctypes.data), C.c_uint64(rays.size), C.c_float(t_min), C.c_int(nthreads),
+                          C.c_void_p(ids.ctypes.data), C.c_void_p(t.ctypes.data))
+        return ids, t
+
+    def node_count(self):
+        return int(self.lib.nw_node_count(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.nw_free.argtypes = [C.c_void_p]
+            self.lib.nw_free(self.h)
+            self.h = C.c_void_p(None)

@@ -278,7 +278,7 @@ int ensure_staging(trq_scene* s, uint64_t chunk) {
 int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits) {
     static const uint64_t chunkRays = [] {
         const char* e = getenv("TRQ_CHUNK_RAYS");
-        long long v = e ? atoll(e) : (2ll << 20);
+        long long v = e ? atoll(e) : (512ll << 10)  /* B200 sweep: 128K..4M rays per chunk, best at 512K (profiles/r01_e2e_chunk_sweep.txt) */;
         return (uint64_t)(v < 1024 ? 1024 : v);
     }();
     std::lock_guard<std::mutex> lock(s->stageMutex);
