@@ -119,6 +119,8 @@ typedef struct trq_scene_info_t {
                                        (chunked, overlapped with tracing) and returns after completion */
 #define TRQ_KERNEL_REFLAYOUT 0x4u   /* run the 1:1 transcription over the reference-layout buffers
                                        (correctness anchor / naive baseline) instead of the packed kernel */
+#define TRQ_SORT_RAYS        0x8u   /* hint: the batch is incoherent; the library may order the work queue by
+                                       (origin cell, direction octant) first. Results are identical either way. */
 
 typedef struct trq_scene trq_scene;
 

@@ -99,3 +99,18 @@ def test_streams_are_reentrant(c3):
     torch.cuda.synchronize()
     for o in outs:
         assert torch.equal(o, ref)
+
+
+def test_sort_hint_changes_nothing_but_order_of_work(c3):
+    """TRQ_SORT_RAYS reorders the work queue only: identical bytes out, for incoherent rays and for the degenerate
+    batch whose rays all start at one point (one histogram bin)."""
+    torch = _torch()
+    from tracer_b200 import harness as H, rays_to_torch
+    prim, scene, rays = c3
+    d = rays_to_torch(rays[:2_000_000], "cuda:0")
+    assert torch.equal(scene.hit(d, sort=True), scene.hit(d))
+    assert torch.equal(scene.hit(d, any=True, sort=True), scene.hit(d, any=True))
+    primary = rays_to_torch(H.cornell_camera_rays(1920, 1080), "cuda:0")
+    assert torch.equal(scene.hit(primary, sort=True), scene.hit(primary))
+    host = scene.hit(rays[:300_000].copy())
+    assert np.array_equal(host.view(np.uint8), scene.hit(rays_to_torch(rays[:300_000], "cuda:0"), sort=True).cpu().numpy().view(np.uint8).reshape(-1))

@@ -37,7 +37,7 @@ def workloads(name):
         bounce, _ = H.bounce_rays(recs)
         return prim, scene, {"primary": prim_rays, "bounce": bounce}
     if name.startswith("soup"):
-        n = {"soup1m": 1_000_000, "soup10m": 10_000_000, "soup100k": 100_000}[name]
+        n = {"soup1m": 1_000_000, "soup10m": 10_000_000, "soup100k": 100_000, "soup4m": 4_000_000}[name]
         t = time.time(); prim = H.scene_soup(n, seed=1, extent=0.004 if n >= 10_000_000 else 0.01); tb = time.time() - t
         scene = Scene(prim, 0)
         print(f"# soup build {tb:.1f}s depth {scene.info['maxDepth']}", file=sys.stderr)

@@ -229,10 +229,30 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         TraceParams P;
         P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
         P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
-        if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));
+        P.order = nullptr;
+        if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));      // the ordering pass is part of the timed traversal
+        // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
+        // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
+        // that does not fit L2); TRQ_SORT_RAYS=0/1 in the environment overrides for experiments.
+        static const int sortEnv = [] { const char* e = getenv("TRQ_SORT_RAYS"); return e ? atoi(e) : -1; }();
+        const bool sortRays = sortEnv >= 0 ? (sortEnv != 0) : ((flags & TRQ_SORT_RAYS) != 0);
+        uint32_t* scratch = nullptr;
+        if (sortRays && n >= 65536) {
+            const size_t words = (size_t)TRQ_SORT_BINS + 2 * (size_t)n;          // hist | keys | order
+            TRQ_CUDA(cudaMallocAsync((void**)&scratch, words * sizeof(uint32_t), st));
+            uint32_t* hist = scratch; uint32_t* keys = scratch + TRQ_SORT_BINS; uint32_t* order = keys + n;
+            TRQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)TRQ_SORT_BINS * sizeof(uint32_t), st));
+            const unsigned gb = (unsigned)((n + 255) / 256);
+            sort_count_kernel<<<gb, 256, 0, st>>>(s->dev, d_rays, n, keys, hist);
+            sort_scan_kernel<<<1, 1024, 0, st>>>(hist);
+            sort_scatter_kernel<<<gb, 256, 0, st>>>(keys, n, hist, order);
+            g_launches += 3;
+            P.order = order;
+        }
         if (any) trace_packed_kernel<true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
         else     trace_packed_kernel<false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
         g_launches++;
+        if (scratch) TRQ_CUDA(cudaFreeAsync(scratch, st));
     }
     if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
     {

@@ -118,10 +118,10 @@ class Scene:
     __del__ = close
 
     # ---- Scene::hit over a batch ------------------------------------------------------------
-    def hit(self, rays, any=False, out=None, reflayout=False, stream=None):
+    def hit(self, rays, any=False, out=None, reflayout=False, stream=None, sort=False):
         """rays: torch CUDA float32 tensor (n, 8) -> returns torch CUDA float32 tensor (n, 8) holding
         trq_hit rows (view as int32 for the id fields); or numpy `ray_dtype` array -> numpy `hit_dtype`."""
-        flags = (L.TRACE_ANY if any else 0) | (L.KERNEL_REFLAYOUT if reflayout else 0)
+        flags = (L.TRACE_ANY if any else 0) | (L.KERNEL_REFLAYOUT if reflayout else 0) | (L.SORT_RAYS if sort else 0)
         if isinstance(rays, np.ndarray):
             if rays.dtype != L.ray_dtype:
                 raise TypeError("host rays must have ray_dtype")
@@ -140,9 +140,9 @@ class Scene:
         check(lib.trq_trace(self._h, rays.data_ptr(), n, flags, hits.data_ptr(), C.c_void_p(st)), "trq_trace")
         return hits
 
-    def hit_host(self, rays_ptr, n, hits_ptr, any=False):
+    def hit_host(self, rays_ptr, n, hits_ptr, any=False, sort=False):
         """Raw host-pointer call (pinned buffers owned by the caller); used by the e2e bench."""
-        flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS
+        flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS | (L.SORT_RAYS if sort else 0)
         check(lib.trq_trace(self._h, rays_ptr, n, flags, hits_ptr, None), "trq_trace")
 
     def profile(self, on=True):
