@@ -37,7 +37,9 @@ UNIT = "Mrays/s"
 HBM_FALLBACK_GBS = 6650.0
 
 WORKLOADS = {
-    "c2": "C2: RT_Metal Cornell box triangles + teapot (15.7k tris), 1920x1080 primary hits -> 1 diffuse bounce batch",
+    "c2": "C2: RT_Metal Cornell box triangles + teapot (15.7k tris), 1920x1080 primary + 1 diffuse bounce, device-resident wavefront (cast, trace, spawn, trace)",
+    "c2bounce": "C2 geometry, only the diffuse bounce batch spawned from the 1920x1080 primary hits",
+    "c3path": "C3 geometry (1.0M tris), 3840x2160 primary + 1 diffuse bounce, device-resident wavefront (cast, trace, spawn, trace)",
     "c3": "C3: RT_Metal meshes scene (coatball+teapot subdivided x16, 1.0M tris), incoherent diffuse bounce rays from 3840x2160 primary hits",
     "c4": "C4: C3 geometry + 10,012 spheres, any-hit shadow rays toward light squares 5/6 from 3840x2160 primary hits",
     "c5": "C5: 10M-triangle random soup, 8M uniform incoherent rays per GPU",
@@ -46,7 +48,16 @@ WORKLOADS = {
 }
 # algorithmic bytes per ray measured once by the instrumented oracle; used only if the
 # oracle cannot be run in this process. Recomputed live on the cpu_baseline sample otherwise.
-BYTES_PER_RAY_FALLBACK = {"c1": 700.0, "c2": 1094.0, "c3": 1778.0, "c4": 2887.0, "c5": 9184.0, "soup1m": 7039.0}
+# device-resident wavefronts: name -> image size (primary rays per step); the Cornell camera of Tracer.mm:371-411
+PATH_WORKLOADS = {"c2": (1920, 1080), "c3path": (3840, 2160)}
+
+
+def L_ray_dtype():
+    from tracer_b200 import layout
+    return layout.ray_dtype
+
+
+BYTES_PER_RAY_FALLBACK = {"c3path": 1400.0, "c2bounce": 1094.0, "c1": 700.0, "c2": 1094.0, "c3": 1778.0, "c4": 2887.0, "c5": 9184.0, "soup1m": 7039.0}
 
 
 def log(*a):
@@ -64,9 +75,9 @@ def peaks():
 # ----------------------------------------------------------------------------------------------- workloads
 def build_scene(name):
     from tracer_b200 import harness as H
-    if name == "c2":
+    if name in ("c2", "c2bounce"):
         return H.scene_c2()
-    if name == "c3":
+    if name in ("c3", "c3path"):
         return H.scene_c3(2)
     if name == "c4":
         return H.scene_c4(2)
@@ -93,7 +104,7 @@ def make_rays_gpu(name, prim, scene, rank, device):
         return H.random_rays(n, seed=2, first=rank * n), False
     if name == "c1":
         return c1_rays(), False
-    W, Hh = (1920, 1080) if name == "c2" else (3840, 2160)
+    W, Hh = (1920, 1080) if name == "c2bounce" else (3840, 2160)
     primary = H.cornell_camera_rays(W, Hh)
     d = rays_to_torch(primary, device)
     recs = scene.expand(d, scene.hit(d)).cpu().numpy().view(L.record_dtype).reshape(-1)
@@ -114,13 +125,16 @@ def make_rays_cpu_sample(name, prim, ref_trace_records, stride):
         return H.random_rays(8_000_000 // stride, seed=2), False
     if name == "c1":
         return c1_rays(), False
-    W, Hh = (1920, 1080) if name == "c2" else (3840, 2160)
+    W, Hh = (1920, 1080) if name in ("c2", "c2bounce") else (3840, 2160)
     primary = H.cornell_camera_rays(W, Hh)[::stride].copy()
     recs = ref_trace_records(primary)
     if name == "c4":
         la, lb = H.scene_c4_lights(prim)
         return H.shadow_rays(recs, la, lb, 0)[0], True
-    return H.bounce_rays(recs, 0)[0], False
+    bounce = H.bounce_rays(recs, 0)[0]
+    if name in PATH_WORKLOADS:                                  # both waves of the wavefront
+        return np.concatenate([primary, bounce]), False
+    return bounce, False
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -288,20 +302,44 @@ def run_gpu_arm(a):
     t_build = time.time() - t0
     prim = D.replicate_primitive(prim, src=0)
     scene = Scene(prim, local_rank)
-    rays, any_hit = make_rays_gpu(a.workload, prim, scene, rank, device)
-    n = rays.size
-    d_rays = rays_to_torch(rays, device)
-    d_hits = torch.empty((n, 8), dtype=torch.float32, device=device)
-    if rank == 0:
-        log(f"# scene {scene.info}, build {t_build:.1f}s, {n} rays/rank")
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if a.flush_l2 else None
-
     # TRQ_SORT_RAYS hint: only for the batch that is incoherent AND whose scene cannot live in L2 (C5)
     sort = (a.workload == "c5") if a.sort is None else bool(a.sort)
+    path = a.workload in PATH_WORKLOADS
+    launches_per_step = 1
+    if path:
+        # device-resident wavefront (BASELINE configs[1]: "primary + 1 diffuse bounce"): castRay for every pixel,
+        # trace, spawn the diffuse bounce of every hit (compacted, count stays on the device), trace that too.
+        W, Hh = PATH_WORKLOADS[a.workload]
+        cam = ((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)))
+        r0 = torch.empty((W * Hh, 8), dtype=torch.float32, device=device); h0 = torch.empty_like(r0)
+        r1 = torch.empty_like(r0); h1 = torch.empty_like(r0)
+        s1 = torch.empty(W * Hh, dtype=torch.int32, device=device); c1 = torch.zeros(1, dtype=torch.int64, device=device)
+        seed_base = rank << 32
+        any_hit, launches_per_step = False, 2
 
-    def step():
-        scene.hit(d_rays, any=any_hit, out=d_hits, sort=sort)
+        def step():
+            scene.cast_rays(*cam, W, Hh, out=r0)
+            scene.hit(r0, out=h0)
+            scene.spawn_bounce(r0, h0, seed_base=seed_base, out=r1, src=s1, count=c1)
+            scene.hit_indirect(r1, c1, out=h1)
+
+        step(); torch.cuda.synchronize()
+        n1 = int(c1.item())
+        n = W * Hh + n1
+        rays = np.concatenate([r0.cpu().numpy().view(L_ray_dtype()).reshape(-1), r1[:n1].cpu().numpy().view(L_ray_dtype()).reshape(-1)])
+        d_hits = torch.cat([h0, h1[:n1]])
+    else:
+        rays, any_hit = make_rays_gpu(a.workload, prim, scene, rank, device)
+        n = rays.size
+        d_rays = rays_to_torch(rays, device)
+        d_hits = torch.empty((n, 8), dtype=torch.float32, device=device)
+
+        def step():
+            scene.hit(d_rays, any=any_hit, out=d_hits, sort=sort)
+    if rank == 0:
+        log(f"# scene {scene.info}, build {t_build:.1f}s, {n} rays/step/rank")
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if a.flush_l2 else None
 
     sampler = ClockSampler(local_rank)                  # runs from before the warm-up to the end of the timed region
     for _ in range(max(a.warmup, 3)):
@@ -342,19 +380,34 @@ def run_gpu_arm(a):
     value = total_rays * a.steps / total_ms / 1e3
 
     # ---- e2e: host (pinned) rays in, host hits out, through the C-ABI host-pointer path
-    h_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).pin_memory()
     h_hits = torch.empty((n, 8), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(a.steps, 20))
+    if path:
+        # inputs are the camera (52 bytes); both hit buffers come back to pinned host memory every step
+        def e2e_step():
+            step()
+            h_hits[: W * Hh].copy_(h0, non_blocking=True)
+            h_hits[W * Hh:].copy_(h1[:n1], non_blocking=True)
+            torch.cuda.synchronize()
+        h2d_bytes, d2h_bytes = 52, int(n * 32)
+    else:
+        h_rays = torch.from_numpy(rays.view(np.float32).reshape(-1, 8)).pin_memory()
+
+        def e2e_step():
+            scene.hit_host(h_rays.data_ptr(), n, h_hits.data_ptr(), any=any_hit, sort=sort)
+        h2d_bytes, d2h_bytes = int(n * 32), int(n * 32)
     for _ in range(2):
-        scene.hit_host(h_rays.data_ptr(), n, h_hits.data_ptr(), any=any_hit, sort=sort)
+        e2e_step()
     D.barrier(); torch.cuda.synchronize()
     t = time.perf_counter()
     for _ in range(e2e_steps):
-        scene.hit_host(h_rays.data_ptr(), n, h_hits.data_ptr(), any=any_hit, sort=sort)
+        e2e_step()
     torch.cuda.synchronize()
     e2e_s = D.max_over_ranks(time.perf_counter() - t)
     e2e_value = total_rays * e2e_steps / e2e_s / 1e6
     # the host path must produce the same bytes as the device path
+    if path:
+        d_hits = torch.cat([h0, h1[:n1]])
     same = bool(torch.equal(h_hits, d_hits.cpu()))
     hit_frac = float((d_hits[:, 7].view(torch.int32) & 1).float().mean())
 
@@ -406,7 +459,7 @@ def run_gpu_arm(a):
     except Exception as e:  # the oracle is test infrastructure: never let it take the GPU numbers down
         log(f"# cpu baseline unavailable: {e!r}")
 
-    trace_ms_avg = trace_ms / max(1, nl)
+    trace_ms_avg = trace_ms / max(1, nl) * launches_per_step          # traversal-kernel time per step
     achieved = bpr * n / (trace_ms_avg * 1e-3) / 1e9 if trace_ms_avg > 0 else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -430,10 +483,11 @@ def run_gpu_arm(a):
                      "peak": peak, "unit": "GB/s", "frac": None if achieved is None else round(achieved / peak, 4),
                      "traffic": traffic, "traffic_unit": "GB per launch (ncu dram__bytes_read+write)",
                      "algorithmic_gb_per_launch": round(bpr * n / 1e9, 3), "peak_source": peak_src, "algorithmic_bytes_per_ray": round(bpr, 1),
-                     "kernel_ms": round(trace_ms_avg, 4), "resolve_kernel_ms": round(resolve_ms / max(1, nl), 4),
+                     "kernel_ms": round(trace_ms_avg, 4), "resolve_kernel_ms": round(resolve_ms / max(1, nl) * launches_per_step, 4),
+                     "trace_launches_per_step": launches_per_step,
                      "kernel_share_of_step": round(trace_ms_avg / max(1e-9, total_ms / a.steps), 4)},
         "cpu_baseline": cpu,
-        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * 32), "d2h_bytes_per_step": int(n * 32),
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "steps": e2e_steps, "host_path_equals_device_path": same, "timing": "wall clock around K synchronous C-ABI calls, max over ranks"},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -143,6 +143,37 @@ int  trq_trace(trq_scene* scene, const trq_ray* rays, uint64_t n, uint32_t flags
 int  trq_expand_hits(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n,
                      uint32_t flags, trq_hit_record* records, void* stream);
 
+/* ---- wavefront callers (the producers either side of the query; device pointers only) ----------------------
+ * With these a cast -> trace -> spawn -> trace ... wavefront stays on the GPU: spawn compacts the surviving rays
+ * into `out` with one atomic per warp and leaves their number in device memory (*d_count), which
+ * trq_trace_indirect and the next spawn read on the device (no host round trip). */
+
+/* Arguments of MakeCamera (RT_Metal/Tracer/Tracer.mm:87-125); vfov in radians, as the reference passes it. */
+typedef struct trq_camera {
+    float lookFrom[3], lookAt[3], viewUp[3];
+    float vfov, aspect, aperture, focus_dist;
+} trq_camera;
+
+/* castRay for every pixel of a W x H image (Camera.hh:59-69 with s = x/W, t = y/H, Render.metal:523-527):
+ * rays[y*W + x], tmax = FLT_MAX. Only aperture 0 (the reference's prepareCamera, Tracer.mm:380). */
+int  trq_cast_rays(trq_scene* scene, const trq_camera* camera, uint32_t W, uint32_t H, trq_ray* rays, void* stream);
+
+/* Scene::hit with the batch size read from device memory: traces min(*d_count, capacity) rays. */
+int  trq_trace_indirect(trq_scene* scene, const trq_ray* rays, const uint64_t* d_count, uint64_t capacity,
+                        uint32_t flags, trq_hit* hits, void* stream);
+
+/* Diffuse bounce of tracePath (Render.metal:447-475): for every hit i < n (n clamped to *d_n when d_n != NULL):
+ * PCG32(seedBase + i, 1) -> uu; origin = offset_ray(p, sn); direction = normalize(stw * CosineSampleHemisphere(uu));
+ * tmax = FLT_MAX. out needs room for n rays; srcIndex (optional) receives i per output ray; *d_count the total. */
+int  trq_spawn_bounce(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n,
+                      uint64_t seedBase, trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream);
+
+/* NEE shadow ray of traceMIS (Render.metal:313-337): toward a point sampled (Square::sample, Square.hh:40-58) on
+ * squareList[lightA] or squareList[lightB] (picked by random() < 0.5), tmax = distance; trace with TRQ_TRACE_ANY. */
+int  trq_spawn_shadow(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n,
+                      uint64_t seedBase, uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex,
+                      uint64_t* d_count, void* stream);
+
 /* Per-kernel timing for roofline reports: when enabled, every device-pointer trq_trace records CUDA
  * events (on the caller's stream) around the traversal kernel and around the resolve kernel.
  * trq_profile_read waits for them and returns the SUMS over the launches since the last read

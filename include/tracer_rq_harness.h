@@ -36,6 +36,10 @@ void trqh_make_soup(uint32_t nTri, uint64_t seed, float extent, void* triList, u
 void trqh_gen_random_rays(uint64_t first, uint64_t n, uint64_t seed, const float lo[3], const float hi[3],
                           float tmax, trq_ray* rays);
 
+/* MakeCamera (Tracer.mm:87-125): out = {lookFrom, u, v, vertical, horizontal, cornerLowLeft}, 3 floats each. */
+void trqh_make_camera(const float lookFrom[3], const float lookAt[3], const float viewUp[3],
+                      float vfov, float aspect, float focus_dist, float out[18]);
+
 /* MakeCamera + castRay with aperture 0: pixel (x,y) -> s = x/W, t = y/H (no jitter), row-major
  * y*W + x. vfov in radians as the reference passes it. */
 void trqh_gen_camera_rays(const float lookFrom[3], const float lookAt[3], const float viewUp[3],

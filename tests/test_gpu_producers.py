@@ -1,0 +1,104 @@
+"""GPU: device-side ray producers (row f-3: castRay, bounce spawn, shadow spawn) and the device-resident wavefront
+(trq_trace_indirect), against the host restatements in csrc/host/harness.cpp -- which tests/test_harness.py checks
+against the reference's own functions -- and against the oracle for the traversal of the produced rays."""
+import numpy as np
+import pytest
+
+from tracer_b200 import layout as L
+
+from .util import bits
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def cornell(built):
+    _torch()
+    from tracer_b200 import Scene, harness as H
+    prim = H.scene_reference_cornell()
+    return prim, Scene(prim, 0)
+
+
+def _np_rays(t, n=None):
+    a = t.detach().cpu().numpy().view(L.ray_dtype).reshape(-1)
+    return a if n is None else a[:n]
+
+
+def test_cast_rays_bit_exact(cornell):
+    from tracer_b200 import harness as H
+    prim, scene = cornell
+    dev = scene.cast_rays((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)), 320, 180)
+    host = H.cornell_camera_rays(320, 180)
+    assert np.array_equal(_np_rays(dev).view(np.uint8), host.view(np.uint8))
+
+
+def test_spawn_bounce_and_shadow_match_host(cornell):
+    torch = _torch()
+    from tracer_b200 import harness as H
+    prim, scene = cornell
+    d = scene.cast_rays((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)), 320, 180)
+    hits = scene.hit(d)
+    recs = scene.expand(d, hits).cpu().numpy().view(L.record_dtype).reshape(-1)
+    for kind in ("bounce", "shadow"):
+        if kind == "bounce":
+            out, src, cnt = scene.spawn_bounce(d, hits, seed_base=11)
+            want, wsrc = H.bounce_rays(recs, seed_base=11)
+        else:
+            out, src, cnt = scene.spawn_shadow(d, hits, 5, 6, seed_base=11)
+            want, wsrc = H.shadow_rays(recs, prim.squareList[5:6], prim.squareList[6:7], seed_base=11)
+        n = int(cnt.item())
+        assert n == want.size == int(recs["hit"].sum())
+        got = _np_rays(out, n)
+        order = np.argsort(src.cpu().numpy()[:n].astype(np.uint32), kind="stable")      # compaction order is warp-arrival order
+        got = got[order]
+        assert np.array_equal(src.cpu().numpy()[:n].astype(np.uint32)[order], wsrc)
+        assert np.array_equal(bits(got["o"]), bits(want["o"])), "offset_ray origins must be bit-exact"
+        # cosf/sinf differ between CUDA and libm by an ulp; CosineSampleHemisphere's z = sqrt(1 - dx^2 - dy^2) is
+        # ill-conditioned at the rim of the disk (an ulp in dx moves z by ~3e-4), hence a bulk and a worst-case bound
+        err = np.abs(got["d"].astype(np.float64) - want["d"].astype(np.float64)).max(axis=1)
+        assert np.quantile(err, 0.99) < 2e-6 and err.max() < 2e-3, (np.quantile(err, 0.99), err.max())
+        if kind == "shadow":
+            assert np.allclose(got["tmax"], want["tmax"], rtol=1e-6)
+            assert np.array_equal(bits(got["d"]), bits(want["d"])), "shadow directions use no libm: bit-exact"
+        else:
+            assert (got["tmax"] == np.float32(L.FLT_MAX)).all()
+
+
+def test_device_wavefront_two_bounces(cornell, port):
+    """cast -> trace -> spawn -> trace_indirect -> spawn(indirect) -> trace_indirect with no host sync in between;
+    every wave is checked bit-exactly against the oracle on the rays the device produced."""
+    torch = _torch()
+    from tracer_b200 import hits_to_numpy
+    prim, scene = cornell
+    W, H = 256, 144
+    r0 = scene.cast_rays((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)), W, H)
+    h0 = scene.hit(r0)
+    r1, s1, c1 = scene.spawn_bounce(r0, h0, seed_base=1)
+    h1 = scene.hit_indirect(r1, c1)
+    r2, s2, c2 = scene.spawn_bounce(r1, h1, seed_base=1 << 20, count_in=c1)
+    h2 = scene.hit_indirect(r2, c2)
+    sh, s3, c3 = scene.spawn_shadow(r1, h1, 5, 6, seed_base=7, count_in=c1)
+    occ = scene.hit_indirect(sh, c3, any=True)
+    torch.cuda.synchronize()
+    n1, n2, n3 = int(c1.item()), int(c2.item()), int(c3.item())
+    assert 0 < n2 < n1 < W * H and n3 == n2                      # every first-bounce hit spawns one bounce and one shadow ray
+    for rays_t, hits_t, n, any_hit in ((r0, h0, W * H, False), (r1, h1, n1, False), (r2, h2, n2, False), (sh, occ, n3, True)):
+        rays = _np_rays(rays_t, n).copy()
+        got = hits_to_numpy(hits_t)[:n]
+        want = port.trace(prim, rays, any=any_hit, nthreads=8)["hits"]
+        for k in ("flags", "pType", "pIndex", "leafNode", "material"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.array_equal(bits(got["t"]), bits(want["t"]))
+    # an indirect count of zero traces nothing and touches nothing
+    zero = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    sentinel = torch.full((64, 8), 7.0, device="cuda:0")
+    scene.hit_indirect(r1[:64].contiguous(), zero, out=sentinel)
+    torch.cuda.synchronize()
+    assert bool((sentinel == 7.0).all())

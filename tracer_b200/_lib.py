@@ -40,16 +40,22 @@ class SceneInfo(C.Structure):
     ]
 
 
+class Camera(C.Structure):
+    _fields_ = [("lookFrom", C.c_float * 3), ("lookAt", C.c_float * 3), ("viewUp", C.c_float * 3),
+                ("vfov", C.c_float), ("aspect", C.c_float), ("aperture", C.c_float), ("focus_dist", C.c_float)]
+
+
 # every symbol include/*.h declares; tests/test_abi.py checks the library exports all of them
 ABI_SYMBOLS = [
     "trq_version", "trq_last_error_string", "trq_device_count",
     "trq_scene_create", "trq_scene_destroy", "trq_scene_info",
     "trq_trace", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read",
     "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree",
+    "trq_cast_rays", "trq_trace_indirect", "trq_spawn_bounce", "trq_spawn_shadow",
 ]
 HARNESS_SYMBOLS = [
     "trqh_pcg32_fill_f32", "trqh_pcg32_fill_u32", "trqh_normalize_rays", "trqh_offset_ray",
-    "trqh_make_soup", "trqh_gen_random_rays", "trqh_gen_camera_rays",
+    "trqh_make_soup", "trqh_gen_random_rays", "trqh_make_camera", "trqh_gen_camera_rays",
     "trqh_gen_bounce_rays", "trqh_gen_shadow_rays",
 ]
 
@@ -66,6 +72,10 @@ lib.trq_trace.argtypes = [_vp, _vp, _u64, _u32, _vp, _vp]
 lib.trq_expand_hits.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp, _vp]
 lib.trq_profile_enable.argtypes = [_vp, C.c_int]
 lib.trq_profile_read.argtypes = [_vp, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]
+lib.trq_cast_rays.argtypes = [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp]
+lib.trq_trace_indirect.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp, _vp]
+lib.trq_spawn_bounce.argtypes = [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]
+lib.trq_spawn_shadow.argtypes = [_vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp]
 lib.trq_bvh_build_node.argtypes = [_vp, _vp, _vp, _i32, _u32, _vp]
 lib.trq_bvh_build_nodes_triangles.argtypes = [_vp, _vp, _u32, _u32, _vp]
 lib.trq_bvh_build_tree.argtypes = [_vp, _u32, C.POINTER(_u32), C.POINTER(_u32)]
@@ -82,6 +92,8 @@ lib.trqh_make_soup.argtypes = [_u32, _u64, _f32, _vp, _vp]
 lib.trqh_make_soup.restype = None
 lib.trqh_gen_random_rays.argtypes = [_u64, _u64, _u64, _vp, _vp, _f32, _vp]
 lib.trqh_gen_random_rays.restype = None
+lib.trqh_make_camera.argtypes = [_vp, _vp, _vp, _f32, _f32, _f32, _vp]
+lib.trqh_make_camera.restype = None
 lib.trqh_gen_camera_rays.argtypes = [_vp, _vp, _vp, _f32, _f32, _f32, _u32, _u32, _vp]
 lib.trqh_gen_camera_rays.restype = None
 lib.trqh_gen_bounce_rays.argtypes = [_vp, _u64, _u64, _vp, _vp]

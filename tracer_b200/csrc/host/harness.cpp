@@ -183,9 +183,9 @@ void trqh_gen_random_rays(uint64_t first, uint64_t n, uint64_t seed, const float
     });
 }
 
-void trqh_gen_camera_rays(const float lookFrom_[3], const float lookAt_[3], const float viewUp_[3],
-                          float vfov, float aspect, float focus_dist, uint32_t W, uint32_t H, trq_ray* rays) {
-    // MakeCamera  Tracer.mm:87-125
+void trqh_make_camera(const float lookFrom_[3], const float lookAt_[3], const float viewUp_[3],
+                      float vfov, float aspect, float focus_dist, float out[18]) {
+    // MakeCamera  Tracer.mm:87-125 (vfov in radians, passed straight through)
     V3 lookFrom{lookFrom_[0], lookFrom_[1], lookFrom_[2]}, lookAt{lookAt_[0], lookAt_[1], lookAt_[2]};
     V3 viewUp{viewUp_[0], viewUp_[1], viewUp_[2]};
     float theta = vfov;
@@ -197,6 +197,16 @@ void trqh_gen_camera_rays(const float lookFrom_[3], const float lookAt_[3], cons
     V3 vertical = (2 * halfHeight * focus_dist) * v;
     V3 horizontal = (2 * halfWidth * focus_dist) * u;
     V3 corner = lookFrom - vertical / 2 - horizontal / 2 - focus_dist * w;
+    const V3 all[6] = {lookFrom, u, v, vertical, horizontal, corner};
+    for (int k = 0; k < 6; ++k) { out[3 * k] = all[k].x; out[3 * k + 1] = all[k].y; out[3 * k + 2] = all[k].z; }
+}
+
+void trqh_gen_camera_rays(const float lookFrom_[3], const float lookAt_[3], const float viewUp_[3],
+                          float vfov, float aspect, float focus_dist, uint32_t W, uint32_t H, trq_ray* rays) {
+    float cam[18];
+    trqh_make_camera(lookFrom_, lookAt_, viewUp_, vfov, aspect, focus_dist, cam);
+    const V3 lookFrom{cam[0], cam[1], cam[2]}, vertical{cam[9], cam[10], cam[11]}, horizontal{cam[12], cam[13], cam[14]},
+             corner{cam[15], cam[16], cam[17]};
     parallel_for((uint64_t)W * H, [&](uint64_t a, uint64_t b) {
         for (uint64_t i = a; i < b; ++i) {
             uint32_t x = (uint32_t)(i % W), y = (uint32_t)(i / W);

@@ -22,6 +22,14 @@
 
 namespace trq {
 
+// Batch size of a launch: `n` from the host, or -- for trq_trace_indirect, where the count was produced on the
+// device by a spawn kernel -- *nPtr clamped to the capacity n.
+__device__ __forceinline__ uint64_t live_count(uint64_t n, const unsigned long long* nPtr) {
+    if (nPtr == nullptr) return n;
+    const unsigned long long m = *nPtr;
+    return m < n ? (uint64_t)m : n;
+}
+
 // ---------------------------------------------------------------------------------------------
 // loads
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
@@ -72,9 +80,10 @@ __device__ __noinline__ bool leaf_square_cube(const RefBVH* __restrict__ bvh, co
 // v0: reference layout, reference control flow.
 template <bool ANY>
 __global__ void __launch_bounds__(128)
-trace_reflayout_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* __restrict__ hits, uint64_t n) {
+trace_reflayout_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* __restrict__ hits, uint64_t n,
+                       const unsigned long long* __restrict__ nPtr) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= live_count(n, nPtr)) return;
     const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
     const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
     const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
@@ -146,6 +155,7 @@ struct TraceParams {
     uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
+    const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -185,9 +195,10 @@ __device__ __forceinline__ uint32_t ray_sort_key(const SceneDev& S, const float4
 // issues a single atomicAdd for the group, so a batch whose rays all share one bin (e.g. primary rays from one
 // eye point) costs n/32 same-address atomics, not n.
 __global__ void __launch_bounds__(256)
-sort_count_kernel(SceneDev S, const trq_ray* __restrict__ rays, uint64_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+sort_count_kernel(SceneDev S, const trq_ray* __restrict__ rays, uint64_t n, const unsigned long long* __restrict__ nPtr,
+                  uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
+    const bool valid = i < live_count(n, nPtr);
     const unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (!valid) return;
     const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
@@ -219,9 +230,10 @@ sort_scan_kernel(uint32_t* __restrict__ hist) {
 }
 
 __global__ void __launch_bounds__(256)
-sort_scatter_kernel(const uint32_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
+sort_scatter_kernel(const uint32_t* __restrict__ keys, uint64_t n, const unsigned long long* __restrict__ nPtr,
+                    uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n;
+    const bool valid = i < live_count(n, nPtr);
     const unsigned vm = __ballot_sync(0xffffffffu, valid);
     if (!valid) return;
     const uint32_t key = keys[i];
@@ -251,6 +263,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     float* const coldf = reinterpret_cast<float*>(cold);
     const unsigned lane = threadIdx.x & 31u;
 
+    const uint64_t N = live_count(P.n, P.nPtr);
     bool active = false, exhausted = false;
     f3 ro = make_f3(0.f, 0.f, 0.f), rinv = make_f3(0.f, 0.f, 0.f);
     float range_y = 0.0f;
@@ -276,10 +289,10 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)want);
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned long long)want >= P.n) exhausted = true;
+            if (base + (unsigned long long)want >= N) exhausted = true;
             if (!active) {
                 const uint64_t slot = base + (uint64_t)__popc(idleMask & ((1u << lane) - 1u));
-                if (slot < P.n) {
+                if (slot < N) {
                     const uint64_t idx = P.order ? (uint64_t)__ldg(P.order + slot) : slot;
                     const float4 r0 = ldg4(reinterpret_cast<const float4*>(P.rays + idx));
                     const float4 r1 = ldg4(reinterpret_cast<const float4*>(P.rays + idx) + 1);
@@ -378,9 +391,9 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
 // ---------------------------------------------------------------------------------------------
 // compact -> trq_hit, in place. One thread per ray, fully coalesced.
 __global__ void __launch_bounds__(256)
-resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n) {
+resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n, const unsigned long long* __restrict__ nPtr) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= live_count(n, nPtr)) return;
     float4* io = reinterpret_cast<float4*>(hits + i);
     const float4 a = io[0], b = io[1];
     trq_hit out;

@@ -174,13 +174,14 @@ int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_i
     return TRQ_OK;
 }
 
-int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, trq_hit* d_hits, cudaStream_t st) {
+int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, trq_hit* d_hits, cudaStream_t st,
+                 const unsigned long long* nPtr = nullptr) {
     if (n == 0) return TRQ_OK;
     constexpr uint64_t kMaxPerLaunch = 1ull << 31;             // the kernels keep a 32-bit ray index per lane
     if (n > kMaxPerLaunch) {
         for (uint64_t off = 0; off < n; off += kMaxPerLaunch) {
             const uint64_t m = (n - off) < kMaxPerLaunch ? (n - off) : kMaxPerLaunch;
-            int rc = launch_trace(s, d_rays + off, m, flags, d_hits + off, st);
+            if (nPtr) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: capacity above 2^31 rays"); int rc = launch_trace(s, d_rays + off, m, flags, d_hits + off, st);
             if (rc != TRQ_OK) return rc;
         }
         return TRQ_OK;
@@ -196,8 +197,8 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         const uint64_t grid = (n + block - 1) / block;
         if (grid > 0x7fffffffull) return trq::fail(TRQ_ERR_INVALID, "trq_trace: batch too large");
         if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));
-        if (any) trace_reflayout_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
-        else     trace_reflayout_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
+        if (any) trace_reflayout_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr);
+        else     trace_reflayout_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr);
         g_launches++;
     } else {
         static const uint32_t refillMin = [] {
@@ -229,7 +230,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         TraceParams P;
         P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
         P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
-        P.order = nullptr;
+        P.order = nullptr; P.nPtr = nPtr;
         if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));      // the ordering pass is part of the timed traversal
         // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
         // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
@@ -243,9 +244,9 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             uint32_t* hist = scratch; uint32_t* keys = scratch + TRQ_SORT_BINS; uint32_t* order = keys + n;
             TRQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)TRQ_SORT_BINS * sizeof(uint32_t), st));
             const unsigned gb = (unsigned)((n + 255) / 256);
-            sort_count_kernel<<<gb, 256, 0, st>>>(s->dev, d_rays, n, keys, hist);
+            sort_count_kernel<<<gb, 256, 0, st>>>(s->dev, d_rays, n, nPtr, keys, hist);
             sort_scan_kernel<<<1, 1024, 0, st>>>(hist);
-            sort_scatter_kernel<<<gb, 256, 0, st>>>(keys, n, hist, order);
+            sort_scatter_kernel<<<gb, 256, 0, st>>>(keys, n, nPtr, hist, order);
             g_launches += 3;
             P.order = order;
         }
@@ -258,7 +259,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     {
         const unsigned block = 256;
         const uint64_t grid = (n + block - 1) / block;
-        resolve_hits_kernel<<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n);
+        resolve_hits_kernel<<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr);
         g_launches++;
     }
     if (prof) TRQ_CUDA(cudaEventRecord(prof[2], st));
@@ -491,6 +492,95 @@ int trq_expand_hits(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint
         return TRQ_OK;
     }
     expand_hits_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(s->dev, rays, hits, records, n);
+    g_launches++;
+    TRQ_CUDA(cudaGetLastError());
+    return TRQ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Wavefront callers: device-side ray producers + a trace whose batch size lives
+// on the device, so that cast -> trace -> spawn -> trace -> ... runs without a host round trip.
+#include "../../include/tracer_rq_harness.h"
+#include "kernels/producers.cuh"
+
+extern "C" {
+
+int trq_trace_indirect(trq_scene* s, const trq_ray* rays, const uint64_t* d_count, uint64_t capacity, uint32_t flags,
+                       trq_hit* hits, void* stream) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: NULL scene");
+    if (flags & TRQ_HOST_PTRS) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: device pointers only");
+    if (capacity == 0) return TRQ_OK;
+    if (!rays || !hits || !d_count) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: NULL argument");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    return launch_trace(s, rays, capacity, flags, hits, (cudaStream_t)stream, (const unsigned long long*)d_count);
+}
+
+int trq_cast_rays(trq_scene* s, const trq_camera* cam, uint32_t W, uint32_t H, trq_ray* rays, void* stream) {
+    if (!s || !cam || !rays) return trq::fail(TRQ_ERR_INVALID, "trq_cast_rays: NULL argument");
+    if (cam->aperture != 0.0f) return trq::fail(TRQ_ERR_INVALID, "trq_cast_rays: only aperture 0 (the reference's setting, Tracer.mm:380) is supported");
+    if ((uint64_t)W * H == 0) return TRQ_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    float c[18];
+    trqh_make_camera(cam->lookFrom, cam->lookAt, cam->viewUp, cam->vfov, cam->aspect, cam->focus_dist, c);   // MakeCamera, host
+    CameraDev cd;
+    for (int k = 0; k < 3; ++k) {
+        cd.lookFrom[k] = c[k]; cd.u[k] = c[3 + k]; cd.v[k] = c[6 + k];
+        cd.vertical[k] = c[9 + k]; cd.horizontal[k] = c[12 + k]; cd.corner[k] = c[15 + k];
+    }
+    cd.lenRadius = cam->aperture / 2;
+    const uint64_t n = (uint64_t)W * H;
+    cast_rays_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cd, W, H, rays);
+    g_launches++;
+    TRQ_CUDA(cudaGetLastError());
+    return TRQ_OK;
+}
+
+static int spawn_common(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n,
+                        uint64_t* d_count, const char* who) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "%s: NULL scene", who);
+    if (!d_count) return trq::fail(TRQ_ERR_INVALID, "%s: NULL d_count", who);
+    if (n && (!rays || !hits)) return trq::fail(TRQ_ERR_INVALID, "%s: NULL rays/hits", who);
+    if (n > (1ull << 32)) return trq::fail(TRQ_ERR_INVALID, "%s: more than 2^32 rays in one call", who);
+
+    return TRQ_OK;
+}
+
+int trq_spawn_bounce(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n, uint64_t seedBase,
+                     trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream) {
+    int rc = spawn_common(s, rays, hits, n, d_n, d_count, "trq_spawn_bounce");
+    if (rc != TRQ_OK) return rc;
+    if (n && !out) return trq::fail(TRQ_ERR_INVALID, "trq_spawn_bounce: NULL out");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TRQ_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (n == 0) return TRQ_OK;
+    spawn_bounce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, rays, hits, n, (const unsigned long long*)d_n, seedBase, out, srcIndex,
+                                                                      (unsigned long long*)d_count);
+
+    g_launches++;
+    TRQ_CUDA(cudaGetLastError());
+    return TRQ_OK;
+}
+
+int trq_spawn_shadow(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n, uint64_t seedBase,
+                     uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream) {
+    int rc = spawn_common(s, rays, hits, n, d_n, d_count, "trq_spawn_shadow");
+    if (rc != TRQ_OK) return rc;
+    if (n && !out) return trq::fail(TRQ_ERR_INVALID, "trq_spawn_shadow: NULL out");
+    if (lightA >= s->info.nSquare || lightB >= s->info.nSquare)
+        return trq::fail(TRQ_ERR_INVALID, "trq_spawn_shadow: light index out of range (nSquare %u)", s->info.nSquare);
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TRQ_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
+    if (n == 0) return TRQ_OK;
+    spawn_shadow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, rays, hits, n, (const unsigned long long*)d_n, seedBase, lightA, lightB, out, srcIndex,
+                                                                      (unsigned long long*)d_count);
     g_launches++;
     TRQ_CUDA(cudaGetLastError());
     return TRQ_OK;

@@ -17,7 +17,7 @@ import ctypes as C
 import numpy as np
 
 from . import layout as L
-from ._lib import SceneDesc, SceneInfo, check, lib
+from ._lib import Camera, SceneDesc, SceneInfo, check, lib
 
 
 def _ptr(a):
@@ -144,6 +144,50 @@ class Scene:
         """Raw host-pointer call (pinned buffers owned by the caller); used by the e2e bench."""
         flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS | (L.SORT_RAYS if sort else 0)
         check(lib.trq_trace(self._h, rays_ptr, n, flags, hits_ptr, None), "trq_trace")
+
+    # ---- wavefront callers (device tensors only) ----------------------------------------------
+    def _stream(self, stream=None):
+        import torch
+        return C.c_void_p(stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
+
+    def cast_rays(self, look_from, look_at, view_up, vfov, W, H, aperture=0.0, focus_dist=10.0, out=None, stream=None):
+        """castRay for every pixel (Camera.hh:59-69, Render.metal:523-527) -> (W*H, 8) CUDA tensor of trq_ray."""
+        import torch
+        cam = Camera()
+        cam.lookFrom[:], cam.lookAt[:], cam.viewUp[:] = look_from, look_at, view_up
+        cam.vfov, cam.aspect, cam.aperture, cam.focus_dist = float(vfov), float(np.float32(W) / np.float32(H)), aperture, focus_dist
+        rays = out if out is not None else torch.empty((W * H, 8), dtype=torch.float32, device=f"cuda:{self.device}")
+        check(lib.trq_cast_rays(self._h, C.byref(cam), W, H, rays.data_ptr(), self._stream(stream)), "trq_cast_rays")
+        return rays
+
+    def hit_indirect(self, rays, count, any=False, out=None, sort=False, stream=None):
+        """Scene::hit over min(*count, len(rays)) rays; `count` is a 1-element int64 CUDA tensor written by spawn_*."""
+        import torch
+        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
+        hits = out if out is not None else torch.empty((rays.shape[0], 8), dtype=torch.float32, device=rays.device)
+        check(lib.trq_trace_indirect(self._h, rays.data_ptr(), count.data_ptr(), rays.shape[0], flags, hits.data_ptr(),
+                                     self._stream(stream)), "trq_trace_indirect")
+        return hits
+
+    def _spawn(self, fn, rays, hits, count_in, seed_base, extra, out, src, count, stream):
+        import torch
+        n = rays.shape[0]
+        dev = rays.device
+        out = out if out is not None else torch.empty((n, 8), dtype=torch.float32, device=dev)
+        src = src if src is not None else torch.empty(n, dtype=torch.int32, device=dev)
+        count = count if count is not None else torch.zeros(1, dtype=torch.int64, device=dev)
+        args = [self._h, rays.data_ptr(), hits.data_ptr(), n, None if count_in is None else count_in.data_ptr(), int(seed_base)]
+        args += list(extra) + [out.data_ptr(), src.data_ptr(), count.data_ptr(), self._stream(stream)]
+        check(fn(*args), fn.__name__)
+        return out, src, count
+
+    def spawn_bounce(self, rays, hits, seed_base=0, count_in=None, out=None, src=None, count=None, stream=None):
+        """Diffuse bounce rays of the hits (Render.metal:447-475), compacted. -> (rays_out, srcIndex, count tensor)."""
+        return self._spawn(lib.trq_spawn_bounce, rays, hits, count_in, seed_base, (), out, src, count, stream)
+
+    def spawn_shadow(self, rays, hits, light_a, light_b, seed_base=0, count_in=None, out=None, src=None, count=None, stream=None):
+        """NEE shadow rays toward squareList[light_a|light_b] (Render.metal:313-337), compacted."""
+        return self._spawn(lib.trq_spawn_shadow, rays, hits, count_in, seed_base, (int(light_a), int(light_b)), out, src, count, stream)
 
     def profile(self, on=True):
         check(lib.trq_profile_enable(self._h, 1 if on else 0), "trq_profile_enable")
