@@ -287,6 +287,9 @@ def config_of(workload, extra=None):
 
 
 def run_gpu_arm(a):
+    # stdout carries exactly ONE line (the JSON); anything libraries print there (e.g. "NCCL version ...") goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
 
     from tracer_b200 import Scene, dist as D, launch_count, rays_to_torch
@@ -494,7 +497,8 @@ def run_gpu_arm(a):
     }
     if gathered is not None:
         line["gathered_hits_checked"] = gathered
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     D.barrier()
     _shutdown()
     return 0

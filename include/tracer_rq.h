@@ -201,6 +201,12 @@ int  trq_bvh_build_nodes_triangles(const void* triList, const uint32_t* idxList,
  * interiors after, parent/left/right = final indices. Sequential variant (deterministic). */
 int  trq_bvh_build_tree(void* bvhList, uint32_t nLeaves, uint32_t* nNodeOut, uint32_t* maxDepthOut);
 
+/* The same build on the GPU (level-synchronous binned SAH, kernels/bvh_build.cuh): same arguments (HOST array in
+ * and out), same node array byte for byte -- splits, child order, numbering, boxes -- except when three or more
+ * primitives share one centroid (the reference then falls back to std::sort, whose order of equal keys is
+ * unspecified). TRQ_ERR_NO_DEVICE without a GPU (use the host builder). */
+int  trq_bvh_build_tree_gpu(void* bvhList, uint32_t nLeaves, int device, uint32_t* nNodeOut, uint32_t* maxDepthOut);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "trq_version", "trq_last_error_string", "trq_device_count",
     "trq_scene_create", "trq_scene_destroy", "trq_scene_info",
     "trq_trace", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read",
-    "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree",
+    "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree", "trq_bvh_build_tree_gpu",
     "trq_cast_rays", "trq_trace_indirect", "trq_spawn_bounce", "trq_spawn_shadow",
 ]
 HARNESS_SYMBOLS = [
@@ -79,6 +79,7 @@ lib.trq_spawn_shadow.argtypes = [_vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp
 lib.trq_bvh_build_node.argtypes = [_vp, _vp, _vp, _i32, _u32, _vp]
 lib.trq_bvh_build_nodes_triangles.argtypes = [_vp, _vp, _u32, _u32, _vp]
 lib.trq_bvh_build_tree.argtypes = [_vp, _u32, C.POINTER(_u32), C.POINTER(_u32)]
+lib.trq_bvh_build_tree_gpu.argtypes = [_vp, _u32, C.c_int, C.POINTER(_u32), C.POINTER(_u32)]
 
 lib.trqh_pcg32_fill_f32.argtypes = [_u64, _u64, _u64, _vp]
 lib.trqh_pcg32_fill_f32.restype = None

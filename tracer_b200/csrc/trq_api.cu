@@ -27,6 +27,12 @@ namespace {
 
 std::atomic<uint64_t> g_launches{0};
 
+}  // namespace
+
+namespace trq { void note_launches(uint64_t n) { g_launches += n; } }   // other translation units (GPU builder)
+
+namespace {
+
 #define TRQ_CUDA(call)                                                                          \
     do {                                                                                        \
         cudaError_t e_ = (call);                                                                \

@@ -66,6 +66,9 @@ class BVHBuilder:
     def __init__(self):
         self._chunks = []
 
+    def leaves(self):
+        return np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=L.bvh_dtype)
+
     def buildNode(self, box_min, box_max, model_matrix, pType, pIndex):
         node = np.zeros(1, dtype=L.bvh_dtype)
         lo = np.ascontiguousarray(box_min, dtype=np.float32)
@@ -84,7 +87,8 @@ class BVHBuilder:
                                                     nodes.ctypes.data), "trq_bvh_build_nodes_triangles")
         self._chunks.append(nodes)
 
-    def buildTree(self):
+    def buildTree(self, gpu=None):
+        """BVH::buildTree. gpu=None: host builder; gpu=<device index>: the same tree built on that GPU."""
         leaves = np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=L.bvh_dtype)
         n = leaves.size
         if n == 0:
@@ -92,7 +96,10 @@ class BVHBuilder:
         nodes = np.zeros(2 * n - 1, dtype=L.bvh_dtype)
         nodes[:n] = leaves
         nNode, depth = C.c_uint32(0), C.c_uint32(0)
-        check(lib.trq_bvh_build_tree(nodes.ctypes.data, n, C.byref(nNode), C.byref(depth)), "trq_bvh_build_tree")
+        if gpu is None:
+            check(lib.trq_bvh_build_tree(nodes.ctypes.data, n, C.byref(nNode), C.byref(depth)), "trq_bvh_build_tree")
+        else:
+            check(lib.trq_bvh_build_tree_gpu(nodes.ctypes.data, n, int(gpu), C.byref(nNode), C.byref(depth)), "trq_bvh_build_tree_gpu")
         self.maxDepth = depth.value
         return nodes[: nNode.value]
 
