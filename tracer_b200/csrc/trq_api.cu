@@ -209,12 +209,12 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     } else {
         static const uint32_t refillMin = [] {
             const char* e = getenv("TRQ_REFILL_MIN");
-            int v = e ? atoi(e) : 12;      // B200 sweep (profiles/): 8..16 is flat within 3% on C3 and the 1M soup
+            int v = e ? atoi(e) : 16;      // B200 sweeps (profiles/r01_sweep*): 12..20 is flat within 2% on C3
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
         static const uint32_t leafBatch = [] {
             const char* e = getenv("TRQ_LEAF_BATCH");
-            int v = e ? atoi(e) : 8;
+            int v = e ? atoi(e) : 12;
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
         static const int blocksPerSMOverride =[] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
