@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Developer tool for compute-sanitizer runs: one small pass over every kernel family (trace packed / reflayout,
+any-hit, sort, resolve, expand, producers, indirect trace, GPU builder) on the mixed-primitive Cornell scene."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from tracer_b200 import Scene, harness as H  # noqa: E402
+from tracer_b200.scene import BVHBuilder  # noqa: E402
+
+prim = H.scene_reference_cornell()
+scene = Scene(prim, 0)
+r0 = scene.cast_rays((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)), 96, 54)
+for refl in (False, True):
+    h0 = scene.hit(r0, reflayout=refl)
+h0 = scene.hit(r0, sort=True) if r0.shape[0] >= 65536 else scene.hit(r0)
+big = torch.cat([r0] * 16)
+scene.hit(big, sort=True)
+scene.expand(r0, h0)
+r1, s1, c1 = scene.spawn_bounce(r0, h0, seed_base=3)
+h1 = scene.hit_indirect(r1, c1)
+sh, s2, c2 = scene.spawn_shadow(r1, h1, 5, 6, seed_base=5, count_in=c1)
+scene.hit_indirect(sh, c2, any=True)
+host = scene.hit(H.random_rays(5000, seed=1, lo=(-245, 0, 0), hi=(800, 555, 555)))
+b = BVHBuilder(); b.buildNodesTriangles(prim.triList, prim.idxList)
+g = b.buildTree(gpu=0)
+torch.cuda.synchronize()
+print("sanitize pass done:", int(c1.item()), int(c2.item()), int((host["flags"] & 1).sum()), g.size)
