@@ -135,7 +135,8 @@ int  trq_scene_destroy(trq_scene* scene);
 int  trq_scene_info(const trq_scene* scene, trq_scene_info_t* info);
 
 /* Scene::hit for n rays. Device pointers unless TRQ_HOST_PTRS; asynchronous on `stream`
- * (a cudaStream_t, NULL = default stream) for device pointers. Re-entrant across streams. */
+ * (a cudaStream_t, NULL = default stream) for device pointers. Re-entrant across streams.
+ * Device rays / hits must be 32-byte aligned (every record is moved with one 256-bit access). */
 int  trq_trace(trq_scene* scene, const trq_ray* rays, uint64_t n, uint32_t flags,
                trq_hit* hits, void* stream);
 

@@ -8,8 +8,9 @@
 //       q2 = { right.mini.xyz, 0 }                 q3 = { right.maxi.xyz, 0 }
 //     Both child boxes live in the parent: one 64-B fetch per from-parent step instead of the
 //     reference's 12 B of links + two scattered 32-B boxes + 8 B of child type (Render.hh:151-160,211-213).
-//   packed triangles 48 B = 3 x float4 per triangle LEAF, in depth-first leaf order:
-//       t0 = { v0.xyz, bits(leafNode) }  t1 = { v1 - v0, 0 }  t2 = { v2 - v0, 0 }
+//   packed triangles: 64-byte records (48 B used = 3 x float4) per triangle LEAF, in depth-first leaf order, so
+//     that a test is one 256-bit + one 128-bit request inside one 64-B-aligned record:
+//       t0 = { v0.xyz, bits(leafNode) }  t1 = { v1 - v0, 0 }  t2 = { v2 - v0, 0 }  (t3 unused)
 //     (the two edge subtractions are the first operations of Triangle::hit_test, Triangle.hh:43-44)
 //   packed spheres 32 B = 2 x float4 per sphere LEAF:
 //       s0 = { center.xyz, radius }      s1 = { bits(leafNode), 0, 0, 0 }

@@ -41,6 +41,12 @@ __device__ __forceinline__ void ldg8(const float4* p, float4& a, float4& b) {
                  : "l"(p));
 }
 
+// 256-bit store (STG.E.256 on sm_100): one request for a whole 32-byte record.
+__device__ __forceinline__ void stg8(void* p, const float4& a, const float4& b) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+}
+
 __device__ __forceinline__ void store_compact(trq_hit* hits, uint64_t i, bool hit, float t, uint32_t leaf,
                                               float u, float v, uint32_t aux) {
     float4 a, b;
@@ -51,8 +57,7 @@ __device__ __forceinline__ void store_compact(trq_hit* hits, uint64_t i, bool hi
     b.x = __uint_as_float(hit ? aux : 0u);
     b.y = __uint_as_float(hit ? 1u : 0u);
     b.z = 0.0f; b.w = 0.0f;
-    float4* out = reinterpret_cast<float4*>(hits + i);
-    out[0] = a; out[1] = b;
+    stg8(hits + i, a, b);
 }
 
 // Leaf tests that read reference-layout structs (rare leaf types: Square, Cube). Out of line and fed with
@@ -145,6 +150,8 @@ trace_reflayout_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* __
 #ifndef TRQ_BLOCK
 #define TRQ_BLOCK 256
 #endif
+
+#define TRQ_TRI_STRIDE 4u      // float4 per packed triangle: 64-byte records (48 used) so that a test is two requests, never three
 
 struct TraceParams {
     const trq_ray* rays;
@@ -294,8 +301,8 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 const uint64_t slot = base + (uint64_t)__popc(idleMask & ((1u << lane) - 1u));
                 if (slot < N) {
                     const uint64_t idx = P.order ? (uint64_t)__ldg(P.order + slot) : slot;
-                    const float4 r0 = ldg4(reinterpret_cast<const float4*>(P.rays + idx));
-                    const float4 r1 = ldg4(reinterpret_cast<const float4*>(P.rays + idx) + 1);
+                    float4 r0, r1;
+                    ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);          // trq_ray is one 32-byte record
                     const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
                     ro = ray.o; rinv = ray.inv;
                     range_y = r0.w;                                        // Render.hh:143  range_t = (FLT_MIN, test_t)
@@ -358,8 +365,10 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 ray.d = make_f3(coldf[COLD_DX * TRQ_BLOCK], coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
                 bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t leaf = 0, a = 0;
                 if (kind == REF_TRI) {
-                    const float4* tp = S.tris + (size_t)TRQ_REF_INDEX(cur) * 3u;
-                    const float4 t0 = ldg4(tp), t1 = ldg4(tp + 1), t2 = ldg4(tp + 2);
+                    const float4* tp = S.tris + (size_t)TRQ_REF_INDEX(cur) * TRQ_TRI_STRIDE;
+                    float4 t0, t1;
+                    ldg8(tp, t0, t1);                                       // one 256-bit + one 128-bit request per test
+                    const float4 t2 = ldg4(tp + 2);
                     leaf = __float_as_uint(t0.w);
                     h = tri_hit(make_f3(t0.x, t0.y, t0.z), make_f3(t1.x, t1.y, t1.z), make_f3(t2.x, t2.y, t2.z),
                                 ray, FLT_MIN, range_y, t, u, v);
@@ -486,7 +495,7 @@ pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ r
         const uint32_t p = bvh[i].pIndex;
         const f3 v0 = ld3(verts[idx[3 * p]].v), v1 = ld3(verts[idx[3 * p + 1]].v), v2 = ld3(verts[idx[3 * p + 2]].v);
         const f3 e1 = sub3(v1, v0), e2 = sub3(v2, v0);       // Triangle.hh:43-44
-        float4* out = tris + (size_t)slot * 3u;
+        float4* out = tris + (size_t)slot * TRQ_TRI_STRIDE;
         out[0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(i));
         out[1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
         out[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);

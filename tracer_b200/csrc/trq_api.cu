@@ -389,7 +389,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     if ((rc = upload(&d_ref, ref.data(), ref.size())) != TRQ_OK) return bail(rc);
     auto bail2 = [&](int code) { cudaFree(d_ref); return bail(code); };
 
-    const size_t nodeBytes = (size_t)info.nInterior * 64, triBytes = (size_t)info.nTri * 48, sphBytes = (size_t)info.nSphere * 32;
+    const size_t nodeBytes = (size_t)info.nInterior * 64, triBytes = (size_t)info.nTri * 16 * TRQ_TRI_STRIDE, sphBytes = (size_t)info.nSphere * 32;
     if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes));
     if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes));
     if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes));
@@ -469,6 +469,8 @@ int trq_trace(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq
     if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_trace: NULL scene");
     if (n == 0) return TRQ_OK;
     if (!rays || !hits) return trq::fail(TRQ_ERR_INVALID, "trq_trace: NULL rays/hits");
+    if (!(flags & TRQ_HOST_PTRS) && ((((uintptr_t)rays) | ((uintptr_t)hits)) & 31u))
+        return trq::fail(TRQ_ERR_INVALID, "trq_trace: device rays/hits must be 32-byte aligned (one record = one 256-bit access)");
     DeviceGuard guard(s->device);
     if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
     if (flags & TRQ_HOST_PTRS) return trace_host(s, rays, n, flags, hits);
@@ -519,6 +521,8 @@ int trq_trace_indirect(trq_scene* s, const trq_ray* rays, const uint64_t* d_coun
     if (flags & TRQ_HOST_PTRS) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: device pointers only");
     if (capacity == 0) return TRQ_OK;
     if (!rays || !hits || !d_count) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: NULL argument");
+    if ((((uintptr_t)rays) | ((uintptr_t)hits)) & 31u)
+        return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: rays/hits must be 32-byte aligned");
     DeviceGuard guard(s->device);
     if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
     return launch_trace(s, rays, capacity, flags, hits, (cudaStream_t)stream, (const unsigned long long*)d_count);
