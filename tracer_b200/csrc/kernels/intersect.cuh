@@ -69,20 +69,23 @@ __device__ __forceinline__ bool front_face(const f3& dir, const f3& gn) { return
 // Precomputing e1/e2 is bit-compatible: those subtractions are the first operations of the test.
 __device__ __forceinline__ bool tri_hit(const f3& v0, const f3& e1, const f3& e2, const RayCtx& r,
                                         float range_x, float range_y, float& t, float& u, float& v) {
+    // Same tests in the same order as the reference, evaluated without early exits: in a warp the lanes that
+    // fail early wait for the slowest lane anyway, and every rejection below is a pure comparison (no side
+    // effects), so and-ing them gives exactly the reference's decision, including its NaN behaviour.
     f3 pvec = cross3(r.d, e2);
     float det = dot3(e1, pvec);
-    if (fabsf(det) < FLT_EPSILON) return false;
+    bool ok = !(fabsf(det) < FLT_EPSILON);                 // Triangle.hh:55 (CULLING undefined)
     float invDet = fdiv(1.0f, det);
     f3 tvec = sub3(r.o, v0);
     float uu = fmul(dot3(tvec, pvec), invDet);
-    if (uu < 0.0f || uu > 1.0f) return false;
+    ok = ok && !(uu < 0.0f || uu > 1.0f);                  // :62
     f3 qvec = cross3(tvec, e1);
     float vv = fmul(dot3(r.d, qvec), invDet);
-    if (vv < 0.0f || fadd(uu, vv) > 1.0f) return false;
+    ok = ok && !(vv < 0.0f || fadd(uu, vv) > 1.0f);        // :66
     float tt = fmul(dot3(e2, qvec), invDet);
-    if (tt > range_y || tt < range_x) return false;       // t == range.y passes (Triangle.hh:71)
-    t = tt; u = uu; v = vv;
-    return true;
+    ok = ok && !(tt > range_y || tt < range_x);            // :71  (t == range.y passes)
+    if (ok) { t = tt; u = uu; v = vv; }
+    return ok;
 }
 
 // Sphere::hit_test  (Sphere.hh:35-75); strict interval.

@@ -257,6 +257,9 @@ sort_scatter_kernel(const uint32_t* __restrict__ keys, uint64_t n, const unsigne
 // lane-major => bank-conflict free) so that the hot loop fits in 48 registers (5 resident CTAs per SM).
 enum : uint32_t { COLD_TEST_T = 0, COLD_BEST, COLD_U, COLD_V, COLD_AUX, COLD_RAY, COLD_DX, COLD_DY, COLD_DZ, COLD_WORDS };
 
+#ifndef TRQ_INTERIOR_UNROLL
+#define TRQ_INTERIOR_UNROLL 2
+#endif
 #ifndef TRQ_MIN_BLOCKS
 #define TRQ_MIN_BLOCKS 5
 #endif
@@ -339,23 +342,26 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 const int nInt = __popc(__ballot_sync(0xffffffffu, onInterior));
                 const int nWait = __popc(__ballot_sync(0xffffffffu, active && !onInterior));
                 if (nInt == 0 || nWait >= (int)P.leafBatch || nWait > nInt) break;
-                if (onInterior) {
-                    const float4* np = S.nodes + (size_t)TRQ_REF_INDEX(cur) * 4u;
-                    float4 q0, q1, q2, q3;
-                    ldg8(np, q0, q1);
-                    ldg8(np + 2, q2, q3);
-                    float tl = range_y, tr = range_y;                     // :157
-                    const bool lt = box_entry(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ro, rinv, range_y, tl);   // :159
-                    const bool rt = box_entry(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ro, rinv, range_y, tr);   // :160
-                    const uint32_t lref = __float_as_uint(q0.w), rref = __float_as_uint(q1.w);
-                    if (!lt && !rt) {                                     // :162-169  pop
-                        pop();
-                    } else {
-                        const bool selLeft = tl < tr;                     // :174 (ties -> right, quirk included)
-                        if (lt && rt) { stk[sp * TRQ_BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
-                        cur = selLeft ? lref : rref;
+#pragma unroll
+                for (int rep = 0; rep < TRQ_INTERIOR_UNROLL; ++rep) {          // steps per vote round
+                    if (active && TRQ_REF_KIND(cur) == REF_INTERIOR) {
+                        const float4* np = S.nodes + (size_t)TRQ_REF_INDEX(cur) * 4u;
+                        float4 q0, q1, q2, q3;
+                        ldg8(np, q0, q1);
+                        ldg8(np + 2, q2, q3);
+                        float tl = range_y, tr = range_y;                     // :157
+                        const bool lt = box_entry(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ro, rinv, range_y, tl);   // :159
+                        const bool rt = box_entry(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ro, rinv, range_y, tr);   // :160
+                        const uint32_t lref = __float_as_uint(q0.w), rref = __float_as_uint(q1.w);
+                        if (!lt && !rt) {                                     // :162-169  pop
+                            pop();
+                        } else {
+                            const bool selLeft = tl < tr;                     // :174 (ties -> right, quirk included)
+                            if (lt && rt) { stk[sp * TRQ_BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
+                            cur = selLeft ? lref : rref;
+                        }
+                        if (cur == TRQ_REF_DONE_WORD) finish();
                     }
-                    if (cur == TRQ_REF_DONE_WORD) finish();
                 }
             }
             if (active && TRQ_REF_KIND(cur) != REF_INTERIOR) {
