@@ -26,6 +26,14 @@ def workloads(name):
         recs = scene.expand(d, scene.hit(d)).cpu().numpy().view(L.record_dtype).reshape(-1)
         bounce, _ = H.bounce_rays(recs)
         return prim, scene, {"primary": prim_rays, "bounce": bounce}
+    if name == "refcornell":
+        prim = H.scene_reference_cornell()
+        scene = Scene(prim, 0)
+        prim_rays = H.cornell_camera_rays(3840, 2160)
+        d = rays_to_torch(prim_rays, "cuda:0")
+        recs = scene.expand(d, scene.hit(d)).cpu().numpy().view(L.record_dtype).reshape(-1)
+        bounce, _ = H.bounce_rays(recs)
+        return prim, scene, {"primary": prim_rays, "bounce": bounce}
     if name.startswith("c3"):
         levels = 2 if name == "c3" else int(name[2:])
         t = time.time(); prim = H.scene_c3(levels); tb = time.time() - t

@@ -264,6 +264,10 @@ enum : uint32_t { COLD_TEST_T = 0, COLD_BEST, COLD_U, COLD_V, COLD_AUX, COLD_RAY
 #define TRQ_MIN_BLOCKS 5
 #endif
 
+#ifdef TRQ_STATS
+__device__ unsigned long long g_stats[8];
+#endif
+
 template <bool ANY>
 __global__ void __launch_bounds__(TRQ_BLOCK, TRQ_MIN_BLOCKS)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
@@ -296,6 +300,9 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         const unsigned idleMask = __ballot_sync(0xffffffffu, !active);
         if (!exhausted && (idleMask == 0xffffffffu || __popc(idleMask) >= (int)P.refillMin)) {
             const int want = __popc(idleMask);
+#ifdef TRQ_STATS
+            if (lane == 0) { atomicAdd(&g_stats[4], 1ull); atomicAdd(&g_stats[5], (unsigned long long)want); }
+#endif
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)want);
             base = __shfl_sync(0xffffffffu, base, 0);
@@ -344,6 +351,10 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 if (nInt == 0 || nWait >= (int)P.leafBatch || nWait > nInt) break;
 #pragma unroll
                 for (int rep = 0; rep < TRQ_INTERIOR_UNROLL; ++rep) {          // steps per vote round
+#ifdef TRQ_STATS
+                    { const unsigned m_ = __ballot_sync(0xffffffffu, active && TRQ_REF_KIND(cur) == REF_INTERIOR);
+                      if (lane == 0 && m_) { atomicAdd(&g_stats[0], 1ull); atomicAdd(&g_stats[1], (unsigned long long)__popc(m_)); } }
+#endif
                     if (active && TRQ_REF_KIND(cur) == REF_INTERIOR) {
                         const float4* np = S.nodes + (size_t)TRQ_REF_INDEX(cur) * 4u;
                         float4 q0, q1, q2, q3;
@@ -364,6 +375,10 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     }
                 }
             }
+#ifdef TRQ_STATS
+            { const unsigned m_ = __ballot_sync(0xffffffffu, active && TRQ_REF_KIND(cur) != REF_INTERIOR);
+              if (lane == 0 && m_) { atomicAdd(&g_stats[2], 1ull); atomicAdd(&g_stats[3], (unsigned long long)__popc(m_)); } }
+#endif
             if (active && TRQ_REF_KIND(cur) != REF_INTERIOR) {
                 const uint32_t kind = TRQ_REF_KIND(cur);
                 RayCtx ray;

@@ -349,6 +349,13 @@ int trq_device_count(void) {
 
 uint64_t trq_launch_count(void) { return g_launches.load(); }
 
+#ifdef TRQ_STATS
+void trq_debug_stats(unsigned long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, trq::g_stats, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(trq::g_stats, z, sizeof z); }
+}
+#endif
+
 int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     if (!d || !out) return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: NULL argument");
     *out = nullptr;
