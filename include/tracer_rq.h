@@ -122,6 +122,10 @@ typedef struct trq_scene_info_t {
 #define TRQ_SORT_RAYS        0x8u   /* hint: the batch is incoherent; the library may order the work queue by
                                        (origin cell, direction octant) first. Results are identical either way. */
 
+#define TRQ_HOST_ASYNC       0x10u  /* with TRQ_HOST_PTRS: return as soon as the copies and kernels are queued; the host
+                                       buffers must stay valid (and should be pinned) until trq_host_sync() returns.
+                                       Consecutive calls then overlap: the next batch's H2D runs under this one's D2H. */
+
 typedef struct trq_scene trq_scene;
 
 int  trq_version(void);
@@ -139,6 +143,9 @@ int  trq_scene_info(const trq_scene* scene, trq_scene_info_t* info);
  * Device rays / hits must be 32-byte aligned (every record is moved with one 256-bit access). */
 int  trq_trace(trq_scene* scene, const trq_ray* rays, uint64_t n, uint32_t flags,
                trq_hit* hits, void* stream);
+
+/* Waits for every TRQ_HOST_ASYNC call issued on this scene. */
+int  trq_host_sync(trq_scene* scene);
 
 /* Fills HitRecord fields p, gn, sn, uv, f, material for hits produced by trq_trace. */
 int  trq_expand_hits(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n,

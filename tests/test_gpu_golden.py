@@ -114,3 +114,18 @@ def test_sort_hint_changes_nothing_but_order_of_work(c3):
     assert torch.equal(scene.hit(primary, sort=True), scene.hit(primary))
     host = scene.hit(rays[:300_000].copy())
     assert np.array_equal(host.view(np.uint8), scene.hit(rays_to_torch(rays[:300_000], "cuda:0"), sort=True).cpu().numpy().view(np.uint8).reshape(-1))
+
+
+def test_async_host_calls_equal_sync(c3):
+    """TRQ_HOST_ASYNC: queued back-to-back calls through the shared staging ring give the bytes of the synchronous path."""
+    torch = _torch()
+    prim, scene, rays = c3
+    sub = np.ascontiguousarray(rays[:1_500_000])
+    want = scene.hit(sub)
+    h_rays = torch.from_numpy(sub.view(np.float32).reshape(-1, 8)).pin_memory()
+    outs = [torch.empty((sub.size, 8), dtype=torch.float32).pin_memory() for _ in range(3)]
+    for o in outs:
+        scene.hit_host(h_rays.data_ptr(), sub.size, o.data_ptr(), asynchronous=True)
+    scene.host_sync()
+    for o in outs:
+        assert np.array_equal(o.numpy().view(np.uint8).reshape(-1), want.view(np.uint8).reshape(-1))

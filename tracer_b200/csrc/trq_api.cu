@@ -84,6 +84,7 @@ struct trq_scene {
     cudaStream_t sH2D = nullptr, sCompute = nullptr, sD2H = nullptr;
     cudaEvent_t evH2D[kStageBufs] = {}, evCompute[kStageBufs] = {}, evD2H[kStageBufs] = {};
     bool stageReady = false;
+    uint64_t stageSeq = 0;        // chunks ever staged (ring position)
     // optional per-kernel timing (trq_profile_enable): events around the trace and resolve kernels
     bool profile = false;
     cudaEvent_t evProf[kProfRing][3] = {};
@@ -286,6 +287,9 @@ int ensure_staging(trq_scene* s, uint64_t chunk) {
         s->stageReady = true;
     }
     if (chunk > s->stageCap) {
+        TRQ_CUDA(cudaStreamSynchronize(s->sH2D));            // asynchronous calls may still be using the old buffers
+        TRQ_CUDA(cudaStreamSynchronize(s->sCompute));
+        TRQ_CUDA(cudaStreamSynchronize(s->sD2H));
         for (int b = 0; b < kStageBufs; ++b) {
             cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
             s->d_stageRays[b] = nullptr; s->d_stageHits[b] = nullptr;
@@ -312,11 +316,12 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, tr
     const uint64_t chunk = n < chunkRays ? n : chunkRays;
     int rc = ensure_staging(s, chunk);
     if (rc != TRQ_OK) return rc;
-    uint64_t done = 0; int c = 0;
+    uint64_t done = 0;
     while (done < n) {
         const uint64_t m = (n - done) < chunk ? (n - done) : chunk;
-        const int b = c % kStageBufs;
-        if (c >= kStageBufs) TRQ_CUDA(cudaStreamWaitEvent(s->sH2D, s->evD2H[b], 0));   // buffer reuse
+        const uint64_t seq = s->stageSeq++;                  // runs across calls: TRQ_HOST_ASYNC calls share the ring
+        const int b = (int)(seq % kStageBufs);
+        if (seq >= (uint64_t)kStageBufs) TRQ_CUDA(cudaStreamWaitEvent(s->sH2D, s->evD2H[b], 0));   // buffer reuse
         TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, s->sH2D));
         TRQ_CUDA(cudaEventRecord(s->evH2D[b], s->sH2D));
         TRQ_CUDA(cudaStreamWaitEvent(s->sCompute, s->evH2D[b], 0));
@@ -326,8 +331,9 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, tr
         TRQ_CUDA(cudaStreamWaitEvent(s->sD2H, s->evCompute[b], 0));
         TRQ_CUDA(cudaMemcpyAsync(hits + done, s->d_stageHits[b], m * sizeof(trq_hit), cudaMemcpyDeviceToHost, s->sD2H));
         TRQ_CUDA(cudaEventRecord(s->evD2H[b], s->sD2H));
-        done += m; ++c;
+        done += m;
     }
+    if (flags & TRQ_HOST_ASYNC) return TRQ_OK;               // the caller collects with trq_host_sync()
     TRQ_CUDA(cudaStreamSynchronize(s->sD2H));
     TRQ_CUDA(cudaStreamSynchronize(s->sCompute));
     return TRQ_OK;
@@ -482,6 +488,16 @@ int trq_trace(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq
     if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
     if (flags & TRQ_HOST_PTRS) return trace_host(s, rays, n, flags, hits);
     return launch_trace(s, rays, n, flags, hits, (cudaStream_t)stream);
+}
+
+int trq_host_sync(trq_scene* s) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_host_sync: NULL scene");
+    DeviceGuard guard(s->device);
+    std::lock_guard<std::mutex> lock(s->stageMutex);
+    if (!s->stageReady) return TRQ_OK;
+    TRQ_CUDA(cudaStreamSynchronize(s->sD2H));
+    TRQ_CUDA(cudaStreamSynchronize(s->sCompute));
+    return TRQ_OK;
 }
 
 int trq_expand_hits(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, uint32_t flags,

@@ -147,9 +147,12 @@ class Scene:
         check(lib.trq_trace(self._h, rays.data_ptr(), n, flags, hits.data_ptr(), C.c_void_p(st)), "trq_trace")
         return hits
 
-    def hit_host(self, rays_ptr, n, hits_ptr, any=False, sort=False):
+    def host_sync(self):
+        check(lib.trq_host_sync(self._h), "trq_host_sync")
+
+    def hit_host(self, rays_ptr, n, hits_ptr, any=False, sort=False, asynchronous=False):
         """Raw host-pointer call (pinned buffers owned by the caller); used by the e2e bench."""
-        flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS | (L.SORT_RAYS if sort else 0)
+        flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS | (L.SORT_RAYS if sort else 0) | (L.HOST_ASYNC if asynchronous else 0)
         check(lib.trq_trace(self._h, rays_ptr, n, flags, hits_ptr, None), "trq_trace")
 
     # ---- wavefront callers (device tensors only) ----------------------------------------------
