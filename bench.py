@@ -480,6 +480,13 @@ def run_gpu_arm(a):
     except Exception as e:  # the oracle is test infrastructure: never let it take the GPU numbers down
         log(f"# cpu baseline unavailable: {e!r}")
 
+    # the memory system as measured on this GPU right now (L2 has no entry in MEASURED_PEAKS.json)
+    try:
+        from tracer_b200 import probe_bandwidth
+        l2_gbs, hbm_read_gbs = probe_bandwidth(local_rank, "l2"), probe_bandwidth(local_rank, "hbm")
+    except Exception as e:
+        log(f"# bandwidth probe failed: {e!r}")
+        l2_gbs = hbm_read_gbs = None
     trace_ms_avg = trace_ms / max(1, nl) * launches_per_step          # traversal-kernel time per step
     achieved = bpr * n / (trace_ms_avg * 1e-3) / 1e9 if trace_ms_avg > 0 else None
     traffic = None
@@ -506,6 +513,9 @@ def run_gpu_arm(a):
                      "algorithmic_gb_per_launch": round(bpr * n / 1e9, 3), "peak_source": peak_src, "algorithmic_bytes_per_ray": round(bpr, 1),
                      "kernel_ms": round(trace_ms_avg, 4), "resolve_kernel_ms": round(resolve_ms / max(1, nl) * launches_per_step, 4),
                      "trace_launches_per_step": launches_per_step,
+                     "l2_read_peak_gbs_measured": None if l2_gbs is None else round(l2_gbs, 1),
+                     "frac_of_l2_peak": None if (l2_gbs is None or achieved is None) else round(achieved / l2_gbs, 4),
+                     "hbm_read_gbs_measured": None if hbm_read_gbs is None else round(hbm_read_gbs, 1),
                      "kernel_share_of_step": round(trace_ms_avg / max(1e-9, total_ms / a.steps), 4)},
         "cpu_baseline": cpu,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,

@@ -189,6 +189,10 @@ int  trq_spawn_shadow(trq_scene* scene, const trq_ray* rays, const trq_hit* hits
 int  trq_profile_enable(trq_scene* scene, int on);
 int  trq_profile_read(trq_scene* scene, uint32_t* nLaunches, float* traceKernelMs, float* resolveKernelMs);
 
+/* Read bandwidth of the memory system as this library's kernels see it (16-byte loads that bypass L1, all SMs, best of
+ * five): which = 0 -> 32 MB working set (L2), which = 1 -> 2 GB working set (HBM). For the roofline report. */
+int  trq_probe_bandwidth(int device, int which, double* gbs);
+
 /* Number of kernel launches issued by this library in this process (bench evidence). */
 uint64_t trq_launch_count(void);
 

@@ -49,7 +49,7 @@ class Camera(C.Structure):
 ABI_SYMBOLS = [
     "trq_version", "trq_last_error_string", "trq_device_count",
     "trq_scene_create", "trq_scene_destroy", "trq_scene_info",
-    "trq_trace", "trq_host_sync", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read",
+    "trq_trace", "trq_host_sync", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read", "trq_probe_bandwidth",
     "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree", "trq_bvh_build_tree_gpu",
     "trq_cast_rays", "trq_trace_indirect", "trq_spawn_bounce", "trq_spawn_shadow",
 ]
@@ -71,6 +71,7 @@ lib.trq_scene_info.argtypes = [_vp, C.POINTER(SceneInfo)]
 lib.trq_trace.argtypes = [_vp, _vp, _u64, _u32, _vp, _vp]
 lib.trq_host_sync.argtypes = [_vp]
 lib.trq_expand_hits.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp, _vp]
+lib.trq_probe_bandwidth.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
 lib.trq_profile_enable.argtypes = [_vp, C.c_int]
 lib.trq_profile_read.argtypes = [_vp, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]
 lib.trq_cast_rays.argtypes = [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp]

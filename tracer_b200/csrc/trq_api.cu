@@ -620,3 +620,56 @@ int trq_spawn_shadow(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uin
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Memory-system probes for the roofline report ("no L2 figure is in MEASURED_PEAKS.json, so the
+// harness must measure it"): read-only 16-byte loads that bypass L1 (ld.global.cg) over a working set that fits in L2
+// (32 MB) or does not (2 GB), all SMs, best of five.
+namespace {
+__global__ void __launch_bounds__(256)
+probe_read_kernel(const uint4* __restrict__ buf, uint64_t n16, int iters, uint32_t* sink) {
+    uint32_t acc = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it)
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 v = __ldcg(buf + i);
+            acc += v.x ^ v.y ^ v.z ^ v.w;
+        }
+    if (acc == 0x12345678u) *sink = acc;          // keeps the loads alive
+}
+}  // namespace
+
+extern "C" int trq_probe_bandwidth(int device, int which, double* gbs) {
+    if (!gbs) return trq::fail(TRQ_ERR_INVALID, "trq_probe_bandwidth: NULL argument");
+    int ndev = trq_device_count();
+    if (ndev <= 0) return trq::fail(TRQ_ERR_NO_DEVICE, "trq_probe_bandwidth: no CUDA device");
+    if (device < 0 || device >= ndev) return trq::fail(TRQ_ERR_INVALID, "trq_probe_bandwidth: device out of range");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    TRQ_CUDA(cudaGetDeviceProperties(&prop, device));
+    const uint64_t bytes = which == 0 ? (32ull << 20) : (2ull << 30);
+    const int iters = which == 0 ? 64 : 2;
+    uint4* buf = nullptr; uint32_t* sink = nullptr;
+    TRQ_CUDA(cudaMalloc((void**)&buf, bytes));
+    if (cudaMalloc((void**)&sink, 4) != cudaSuccess) { cudaFree(buf); return trq::fail(TRQ_ERR_CUDA, "cudaMalloc failed"); }
+    cudaMemset(buf, 1, bytes);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const unsigned grid = (unsigned)prop.multiProcessorCount * 8u;
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        probe_read_kernel<<<grid, 256>>>(buf, bytes / 16, iters, sink);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.0f; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+        g_launches++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(buf); cudaFree(sink);
+    if (e != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "trq_probe_bandwidth: %s", cudaGetErrorString(e));
+    *gbs = (double)bytes * iters / (best * 1e-3) / 1e9;
+    return TRQ_OK;
+}

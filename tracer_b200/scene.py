@@ -234,5 +234,12 @@ def rays_to_torch(rays, device):
     return torch.from_numpy(np.ascontiguousarray(rays).view(np.float32).reshape(-1, 8)).to(device)
 
 
+def probe_bandwidth(device=0, which="l2"):
+    """Measured read bandwidth in GB/s: "l2" (32 MB working set) or "hbm" (2 GB)."""
+    g = C.c_double(0)
+    check(lib.trq_probe_bandwidth(int(device), 0 if which == "l2" else 1, C.byref(g)), "trq_probe_bandwidth")
+    return g.value
+
+
 def launch_count():
     return int(lib.trq_launch_count())
