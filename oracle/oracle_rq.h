@@ -125,7 +125,7 @@ void orq_trace(const orq_prims* prims, const orq_ray* rays, uint64_t n, int any,
                orq_hit* hits, orq_record* recs, orq_counters* cnts, orq_totals* totals);
 
 /* algorithmic bytes from totals: 60*N_fp + 12*N_fc + 8*N_disp + 48*N_tri + 16*N_sph + 48*n_rays
- * (+ 32 per square test, + 96 per cube test: fields those tests read) */
+ * (+ 32 per square test, + 160 per cube test: the fields those tests read) */
 uint64_t orq_algorithmic_bytes(const orq_totals* totals, uint64_t n_rays);
 
 #ifdef __cplusplus
