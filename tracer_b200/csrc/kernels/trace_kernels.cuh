@@ -283,13 +283,19 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     float range_y = 0.0f;
     uint32_t cur = TRQ_REF_DONE_WORD, sp = 0;
 
-    // ray finished: write the compact result (resolved into trq_hit by resolve_hits_kernel)
-    auto finish = [&]() {
-        const uint32_t best = cold[COLD_BEST * TRQ_BLOCK];
-        const bool hit = (range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) && best != 0xffffffffu;   // Render.hh:251
-        store_compact(P.hits, cold[COLD_RAY * TRQ_BLOCK], hit, range_y, best,
-                      coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK]);
-        active = false;
+    // A finished ray only retires its lane; its compact result (resolved into trq_hit by resolve_hits_kernel) is
+    // written by flush() when the warp next refills, for all retired lanes at once: the six shared-memory reads and the
+    // store are then issued once per refill instead of once per finishing ray (most rays finish alone in their warp step).
+    bool pending = false;
+    auto finish = [&]() { active = false; pending = true; };
+    auto flush = [&]() {
+        if (pending) {
+            const uint32_t best = cold[COLD_BEST * TRQ_BLOCK];
+            const bool hit = (range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) && best != 0xffffffffu;   // Render.hh:251
+            store_compact(P.hits, cold[COLD_RAY * TRQ_BLOCK], hit, range_y, best,
+                          coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK]);
+            pending = false;
+        }
     };
     auto pop = [&]() {
         if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * TRQ_BLOCK]; }
@@ -307,6 +313,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)want);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base + (unsigned long long)want >= N) exhausted = true;
+            flush();
             if (!active) {
                 const uint64_t slot = base + (uint64_t)__popc(idleMask & ((1u << lane) - 1u));
                 if (slot < N) {
@@ -334,7 +341,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             }
         }
         const unsigned actMask = __ballot_sync(0xffffffffu, active);
-        if (actMask == 0u) { if (exhausted) break; else continue; }
+        if (actMask == 0u) { if (exhausted) { flush(); break; } else continue; }
 
         // ---- traverse until enough lanes have retired to make a refill worthwhile ----
         // Two phases per round so that the (rarer) leaf code is not issued on every interior step:
