@@ -436,6 +436,29 @@ def run_gpu_arm(a):
     same = bool(torch.equal(h_hits, d_hits.cpu()))
     hit_frac = float((d_hits[:, 7].view(torch.int32) & 1).float().mean())
 
+    # ---- multi-GPU, second figure (SURVEY 8d "with and without hit all-gather"): every rank ends up with every rank's
+    # hit records; the all-gather runs chunk by chunk on a second stream under the tracing of the next chunk.
+    with_gather = None
+    if world > 1 and not path:
+        n_common = int(-D.max_over_ranks(-float(n)))                      # ranks trace slightly different batch sizes
+        g_rays = d_rays[:n_common].contiguous()
+        g_local = torch.empty((n_common, 8), dtype=torch.float32, device=device)
+        g_all = torch.empty((world, n_common, 8), dtype=torch.float32, device=device)
+        g_steps = max(3, min(a.steps, 50))
+        for _ in range(3):
+            D.trace_and_gather(scene, g_rays, g_local, g_all, any=any_hit, sort=sort)
+        D.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(g_steps):
+            D.trace_and_gather(scene, g_rays, g_local, g_all, any=any_hit, sort=sort)
+        e1.record(); torch.cuda.synchronize()
+        g_ms = D.max_over_ranks(e0.elapsed_time(e1))
+        ok = bool(torch.equal(g_all[rank], d_hits[:n_common]))
+        with_gather = {"value": round(n_common * world * g_steps / g_ms / 1e3, 2), "unit": UNIT, "steps": g_steps,
+                       "ms_per_step": round(g_ms / g_steps, 4), "gathered_bytes_per_rank_per_step": int(n_common * world * 32),
+                       "chunks": 4, "own_shard_matches": ok}
+
     # ---- multi-GPU: scene checksum agreement + gathered hit count (not timed)
     gathered = None
     if world > 1:
@@ -534,6 +557,8 @@ def run_gpu_arm(a):
         line["e2e_pipelined"] = e2e_pipe
     if gathered is not None:
         line["gathered_hits_checked"] = gathered
+    if with_gather is not None:
+        line["with_hit_allgather"] = with_gather
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     D.barrier()

@@ -135,3 +135,38 @@ def barrier():
     import torch.distributed as dist
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
+
+
+def trace_and_gather(scene, rays, hits_local, hits_all, any=False, sort=False, chunks=4, comm_stream=None):
+    """Trace this rank's rays chunk by chunk and all-gather each chunk's 32-byte hit records while the next chunk is
+    being traced ("chunked and overlapped with tracing on a second stream").
+
+    rays (n, 8) and hits_local (n, 8) are this rank's CUDA tensors; hits_all is (world, n, 8): after the call
+    hits_all[r] holds rank r's hits (every rank must pass the same n). Returns the last NCCL work handle (already waited).
+    """
+    import torch
+    import torch.distributed as dist
+    n = rays.shape[0]
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        scene.hit(rays, any=any, out=hits_local, sort=sort)
+        hits_all[0].copy_(hits_local)
+        return None
+    comm_stream = comm_stream or torch.cuda.Stream(device=rays.device)
+    bounds = [(n * c) // chunks for c in range(chunks + 1)]
+    works = []
+    for c in range(chunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        if hi == lo:
+            continue
+        scene.hit(rays[lo:hi], any=any, out=hits_local[lo:hi], sort=sort)
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ev)
+            outs = [hits_all[r, lo:hi] for r in range(world)]
+            works.append(dist.all_gather(outs, hits_local[lo:hi], async_op=True))
+    for w in works:
+        w.wait()
+    torch.cuda.current_stream(rays.device).wait_stream(comm_stream)
+    return works[-1] if works else None
