@@ -129,3 +129,55 @@ def test_async_host_calls_equal_sync(c3):
     scene.host_sync()
     for o in outs:
         assert np.array_equal(o.numpy().view(np.uint8).reshape(-1), want.view(np.uint8).reshape(-1))
+
+
+def test_c4_any_hit_full_scene(built, port):
+    """BASELINE C4: C3 geometry + 10,012 sphere leaves, any-hit shadow rays toward the light squares with
+    tmax = distance to the light sample; occlusion flag AND the primitive found are bit-exact (the traversal
+    order is the reference's, so the first accepted hit is the same one)."""
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H, hits_to_numpy, rays_to_torch
+    prim = H.scene_c4(2)
+    scene = Scene(prim, 0)
+    assert scene.info["nSphere"] == 10_012 and scene.info["nTri"] > 1_000_000
+    primary = H.cornell_camera_rays(1920, 1080)
+    d = rays_to_torch(primary, "cuda:0")
+    recs = scene.expand(d, scene.hit(d)).cpu().numpy().view(L.record_dtype).reshape(-1)
+    la, lb = H.scene_c4_lights(prim)
+    shadow, _ = H.shadow_rays(recs, la, lb, 0)
+    assert shadow.size > 1_000_000
+    ds = rays_to_torch(shadow, "cuda:0")
+    a = scene.hit(ds, any=True)
+    assert torch.equal(a, scene.hit(ds, any=True, reflayout=True))
+    got = hits_to_numpy(a)
+    occluded = (got["flags"] & 1) == 1
+    assert 0.05 < occluded.mean() < 0.95                         # a real mix of lit and shadowed points
+    assert bool((got["t"][occluded] < shadow["tmax"][occluded]).all())
+    sub = np.ascontiguousarray(shadow[::23])
+    want = port.trace(prim, sub, any=True, nthreads=8)["hits"]
+    g = got[::23]
+    for k in ("flags", "pType", "pIndex", "leafNode", "material"):
+        assert np.array_equal(g[k], want[k]), k
+    assert np.array_equal(bits(g["t"]), bits(want["t"]))
+    # closest-hit over the same rays can only be nearer or equal, and agrees on occlusion
+    c = hits_to_numpy(scene.hit(ds))
+    assert np.array_equal(c["flags"] & 1, got["flags"] & 1)
+    assert bool((c["t"][occluded] <= got["t"][occluded]).all())
+
+
+def test_c1_sphere_scene_full_batch(built, port):
+    """BASELINE C1: the 485-sphere randomScene as Sphere leaves, all 921,600 primary rays against the oracle."""
+    _torch()
+    from tracer_b200 import Scene, harness as H, hits_to_numpy, rays_to_torch
+    prim = H.scene_c1()
+    scene = Scene(prim, 0)
+    rays = H.camera_rays((13, 2, 3), (0, 0, 0), np.float32(20 * np.pi / 180), 1280, 720)
+    assert rays.size == 921_600
+    got = hits_to_numpy(scene.hit(rays_to_torch(rays, "cuda:0")))
+    want = port.trace(prim, rays, nthreads=8)["hits"]
+    for k in ("flags", "pType", "pIndex", "leafNode", "material"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(bits(got["t"]), bits(want["t"]))
+    hit = (want["flags"] & 1) == 1
+    assert np.allclose(got["u"][hit], want["u"][hit], rtol=0, atol=1e-5)      # sphere uv: atan2f / asinf (libm vs CUDA)
+    assert np.allclose(got["v"][hit], want["v"][hit], rtol=0, atol=1e-5)

@@ -428,8 +428,10 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
 // ---------------------------------------------------------------------------------------------
 // compact -> trq_hit, in place. One thread per ray, fully coalesced.
 __global__ void __launch_bounds__(256)
-resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n, const unsigned long long* __restrict__ nPtr) {
+resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n, const unsigned long long* __restrict__ nPtr,
+                    unsigned long long* queueHead) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && queueHead) *queueHead = 0ull;        // the trace that used this queue head finished before this kernel started
     if (i >= live_count(n, nPtr)) return;
     float4* io = reinterpret_cast<float4*>(hits + i);
     const float4 a = io[0], b = io[1];

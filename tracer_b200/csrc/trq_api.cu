@@ -51,8 +51,11 @@ struct DeviceGuard {
 };
 
 constexpr int kCounterRing = 256;
-constexpr int kStageBufs = 3;
+constexpr int kStageBufs = 4;
 constexpr int kProfRing = 64;
+#ifndef TRQ_DEFAULT_CHUNK_RAYS
+#define TRQ_DEFAULT_CHUNK_RAYS (512ll << 10)
+#endif
 
 }  // namespace
 
@@ -73,16 +76,17 @@ struct trq_scene {
     float4* d_sph = nullptr;
     SceneDev dev{};
     uint32_t stackDepth = 1;
+    size_t traceSmem = 0;
+    int blocksPerSM[2] = {0, 0};  // resident trace_packed_kernel CTAs per SM: [closest-hit, any-hit]
     // ray-queue heads
     unsigned long long* d_counters = nullptr;
     std::atomic<uint32_t> counterNext{0};
     // staging for TRQ_HOST_PTRS
     std::mutex stageMutex;
     uint64_t stageCap = 0;
-    trq_ray* d_stageRays[kStageBufs] = {nullptr, nullptr, nullptr};
-    trq_hit* d_stageHits[kStageBufs] = {nullptr, nullptr, nullptr};
-    cudaStream_t sH2D = nullptr, sCompute = nullptr, sD2H = nullptr;
-    cudaEvent_t evH2D[kStageBufs] = {}, evCompute[kStageBufs] = {}, evD2H[kStageBufs] = {};
+    trq_ray* d_stageRays[kStageBufs] = {};
+    trq_hit* d_stageHits[kStageBufs] = {};
+    cudaStream_t stageStream[kStageBufs] = {};   // one stream per staging buffer: copy in, trace, copy out in stream order
     bool stageReady = false;
     uint64_t stageSeq = 0;        // chunks ever staged (ring position)
     // optional per-kernel timing (trq_profile_enable): events around the trace and resolve kernels
@@ -101,15 +105,10 @@ void free_scene(trq_scene* s) {
     cudaFree(s->d_counters);
     for (int b = 0; b < kStageBufs; ++b) {
         cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
-        if (s->evH2D[b]) cudaEventDestroy(s->evH2D[b]);
-        if (s->evCompute[b]) cudaEventDestroy(s->evCompute[b]);
-        if (s->evD2H[b]) cudaEventDestroy(s->evD2H[b]);
+        if (s->stageStream[b]) cudaStreamDestroy(s->stageStream[b]);
     }
     for (int k = 0; k < kProfRing; ++k)
         for (int j = 0; j < 3; ++j) if (s->evProf[k][j]) cudaEventDestroy(s->evProf[k][j]);
-    if (s->sH2D) cudaStreamDestroy(s->sH2D);
-    if (s->sCompute) cudaStreamDestroy(s->sCompute);
-    if (s->sD2H) cudaStreamDestroy(s->sD2H);
     delete s;
 }
 
@@ -186,14 +185,16 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     if (n == 0) return TRQ_OK;
     constexpr uint64_t kMaxPerLaunch = 1ull << 31;             // the kernels keep a 32-bit ray index per lane
     if (n > kMaxPerLaunch) {
+        if (nPtr) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: capacity above 2^31 rays");
         for (uint64_t off = 0; off < n; off += kMaxPerLaunch) {
             const uint64_t m = (n - off) < kMaxPerLaunch ? (n - off) : kMaxPerLaunch;
-            if (nPtr) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: capacity above 2^31 rays"); int rc = launch_trace(s, d_rays + off, m, flags, d_hits + off, st);
+            const int rc = launch_trace(s, d_rays + off, m, flags, d_hits + off, st);
             if (rc != TRQ_OK) return rc;
         }
         return TRQ_OK;
     }
     const bool any = (flags & TRQ_TRACE_ANY) != 0;
+    unsigned long long* usedCounter = nullptr;
     cudaEvent_t* prof = nullptr;
     if (s->profile) {
         prof = s->evProf[s->profHead % kProfRing];
@@ -219,21 +220,15 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
         static const int blocksPerSMOverride =[] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
-        const size_t smem = ((size_t)s->stackDepth + COLD_WORDS) * TRQ_BLOCK * sizeof(uint32_t);
-        if (smem > 48 * 1024) {
-            TRQ_CUDA(cudaFuncSetAttribute(trace_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            TRQ_CUDA(cudaFuncSetAttribute(trace_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-        int perSM = 0;
-        if (any) TRQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, trace_packed_kernel<true>, TRQ_BLOCK, smem));
-        else     TRQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, trace_packed_kernel<false>, TRQ_BLOCK, smem));
-        if (perSM < 1) return trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", smem);
+        const size_t smem = s->traceSmem;
+        int perSM = s->blocksPerSM[any ? 1 : 0];                                 // queried once, in trq_scene_create
         if (blocksPerSMOverride > 0 && blocksPerSMOverride < perSM) perSM = blocksPerSMOverride;
         uint64_t grid = (uint64_t)perSM * (uint64_t)s->numSMs;             // persistent: a multiple of the SM count
         const uint64_t need = (n + TRQ_BLOCK - 1) / TRQ_BLOCK;
         if (grid > need) grid = need;
+        // queue heads are zero at creation and re-zeroed by the resolve kernel that follows each trace on the stream
         unsigned long long* counter = s->d_counters + (s->counterNext.fetch_add(1) % kCounterRing);
-        TRQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        usedCounter = counter;
         TraceParams P;
         P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
         P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
@@ -266,7 +261,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     {
         const unsigned block = 256;
         const uint64_t grid = (n + block - 1) / block;
-        resolve_hits_kernel<<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr);
+        resolve_hits_kernel<<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr, usedCounter);
         g_launches++;
     }
     if (prof) TRQ_CUDA(cudaEventRecord(prof[2], st));
@@ -274,22 +269,42 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     return TRQ_OK;
 }
 
+#ifdef TRQ_STAGE_TIMELINE
+// developer instrumentation (make EXTRA=-DTRQ_STAGE_TIMELINE): device timestamps around every staged operation
+std::vector<cudaEvent_t> g_tl;
+cudaEvent_t* timeline_events(int k) {
+    const size_t at = g_tl.size();
+    g_tl.resize(at + k);
+    for (int i = 0; i < k; ++i) cudaEventCreate(&g_tl[at + i]);
+    return &g_tl[at];
+}
+void timeline_dump() {
+    if (getenv("TRQ_STAGE_TIMELINE_PRINT"))
+        for (size_t i = 0; i + 3 < g_tl.size(); i += 4) {
+            float a, b, c, d;
+            cudaEventElapsedTime(&a, g_tl[0], g_tl[i]); cudaEventElapsedTime(&b, g_tl[0], g_tl[i + 1]);
+            cudaEventElapsedTime(&c, g_tl[0], g_tl[i + 2]); cudaEventElapsedTime(&d, g_tl[0], g_tl[i + 3]);
+            fprintf(stderr, "chunk %3zu  h2d %8.1f..%8.1f  trace ..%8.1f  d2h ..%8.1f us\n", i / 4, a * 1e3, b * 1e3, c * 1e3, d * 1e3);
+        }
+    for (cudaEvent_t e : g_tl) cudaEventDestroy(e);
+    g_tl.clear();
+}
+#endif
+
+int sync_staging(trq_scene* s) {
+    for (int b = 0; b < kStageBufs; ++b)
+        if (s->stageStream[b]) TRQ_CUDA(cudaStreamSynchronize(s->stageStream[b]));
+    return TRQ_OK;
+}
+
 int ensure_staging(trq_scene* s, uint64_t chunk) {
     if (!s->stageReady) {
-        TRQ_CUDA(cudaStreamCreateWithFlags(&s->sH2D, cudaStreamNonBlocking));
-        TRQ_CUDA(cudaStreamCreateWithFlags(&s->sCompute, cudaStreamNonBlocking));
-        TRQ_CUDA(cudaStreamCreateWithFlags(&s->sD2H, cudaStreamNonBlocking));
-        for (int b = 0; b < kStageBufs; ++b) {
-            TRQ_CUDA(cudaEventCreateWithFlags(&s->evH2D[b], cudaEventDisableTiming));
-            TRQ_CUDA(cudaEventCreateWithFlags(&s->evCompute[b], cudaEventDisableTiming));
-            TRQ_CUDA(cudaEventCreateWithFlags(&s->evD2H[b], cudaEventDisableTiming));
-        }
+        for (int b = 0; b < kStageBufs; ++b) TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageStream[b], cudaStreamNonBlocking));
         s->stageReady = true;
     }
     if (chunk > s->stageCap) {
-        TRQ_CUDA(cudaStreamSynchronize(s->sH2D));            // asynchronous calls may still be using the old buffers
-        TRQ_CUDA(cudaStreamSynchronize(s->sCompute));
-        TRQ_CUDA(cudaStreamSynchronize(s->sD2H));
+        int rc = sync_staging(s);                             // asynchronous calls may still be using the old buffers
+        if (rc != TRQ_OK) return rc;
         for (int b = 0; b < kStageBufs; ++b) {
             cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
             s->d_stageRays[b] = nullptr; s->d_stageHits[b] = nullptr;
@@ -304,12 +319,13 @@ int ensure_staging(trq_scene* s, uint64_t chunk) {
     return TRQ_OK;
 }
 
-// Host-pointer path: H2D of rays, trace, D2H of hits, pipelined over chunks on three streams so
-// that PCIe in both directions overlaps the kernels.
+// Host-pointer path: the batch is cut into chunks; chunk k goes through staging buffer k % kStageBufs on that
+// buffer's own stream (copy in, trace, copy out, in stream order). Different chunks overlap on the two copy engines
+// and the SMs, buffer reuse is ordered by the stream itself, and a chunk costs four driver calls.
 int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits) {
-    static const uint64_t chunkRays = [] {
+    const uint64_t chunkRays = [] {                           // read per call so that one process can sweep it
         const char* e = getenv("TRQ_CHUNK_RAYS");
-        long long v = e ? atoll(e) : (512ll << 10)  /* B200 sweep: 128K..4M rays per chunk, best at 512K (profiles/r01_e2e_chunk_sweep.txt) */;
+        long long v = e ? atoll(e) : (TRQ_DEFAULT_CHUNK_RAYS)  /* B200 sweep: profiles/r01_e2e_chunk_sweep.txt */;
         return (uint64_t)(v < 1024 ? 1024 : v);
     }();
     std::lock_guard<std::mutex> lock(s->stageMutex);
@@ -319,24 +335,31 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, tr
     uint64_t done = 0;
     while (done < n) {
         const uint64_t m = (n - done) < chunk ? (n - done) : chunk;
-        const uint64_t seq = s->stageSeq++;                  // runs across calls: TRQ_HOST_ASYNC calls share the ring
-        const int b = (int)(seq % kStageBufs);
-        if (seq >= (uint64_t)kStageBufs) TRQ_CUDA(cudaStreamWaitEvent(s->sH2D, s->evD2H[b], 0));   // buffer reuse
-        TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, s->sH2D));
-        TRQ_CUDA(cudaEventRecord(s->evH2D[b], s->sH2D));
-        TRQ_CUDA(cudaStreamWaitEvent(s->sCompute, s->evH2D[b], 0));
-        rc = launch_trace(s, s->d_stageRays[b], m, flags, s->d_stageHits[b], s->sCompute);
+        const int b = (int)(s->stageSeq++ % kStageBufs);       // runs across calls: TRQ_HOST_ASYNC calls share the ring
+        cudaStream_t st = s->stageStream[b];
+#ifdef TRQ_STAGE_TIMELINE
+        cudaEvent_t* tl = timeline_events(4); cudaEventRecord(tl[0], st);
+#endif
+        TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, st));
+#ifdef TRQ_STAGE_TIMELINE
+        cudaEventRecord(tl[1], st);
+#endif
+        rc = launch_trace(s, s->d_stageRays[b], m, flags, s->d_stageHits[b], st);
         if (rc != TRQ_OK) return rc;
-        TRQ_CUDA(cudaEventRecord(s->evCompute[b], s->sCompute));
-        TRQ_CUDA(cudaStreamWaitEvent(s->sD2H, s->evCompute[b], 0));
-        TRQ_CUDA(cudaMemcpyAsync(hits + done, s->d_stageHits[b], m * sizeof(trq_hit), cudaMemcpyDeviceToHost, s->sD2H));
-        TRQ_CUDA(cudaEventRecord(s->evD2H[b], s->sD2H));
+#ifdef TRQ_STAGE_TIMELINE
+        cudaEventRecord(tl[2], st);
+#endif
+        TRQ_CUDA(cudaMemcpyAsync(hits + done, s->d_stageHits[b], m * sizeof(trq_hit), cudaMemcpyDeviceToHost, st));
+#ifdef TRQ_STAGE_TIMELINE
+        cudaEventRecord(tl[3], st);
+#endif
         done += m;
     }
+#ifdef TRQ_STAGE_TIMELINE
+    sync_staging(s); timeline_dump();
+#endif
     if (flags & TRQ_HOST_ASYNC) return TRQ_OK;               // the caller collects with trq_host_sync()
-    TRQ_CUDA(cudaStreamSynchronize(s->sD2H));
-    TRQ_CUDA(cudaStreamSynchronize(s->sCompute));
-    return TRQ_OK;
+    return sync_staging(s);
 }
 
 }  // namespace
@@ -407,6 +430,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes));
     if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes));
     if (cudaMalloc((void**)&s->d_counters, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(counters) failed"));
+    if (cudaMemset(s->d_counters, 0, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMemset(counters) failed"));
 
     {
         const unsigned block = 256, grid = (d->nNode + block - 1) / block;
@@ -426,6 +450,19 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = N[0].bBOX.mini[k]; s->dev.rootMax[k] = N[0].bBOX.maxi[k]; }
     s->dev.nNode = d->nNode;
     s->stackDepth = info.maxDepth + 1;
+    s->traceSmem = ((size_t)s->stackDepth + COLD_WORDS) * TRQ_BLOCK * sizeof(uint32_t);
+    {
+        cudaError_t e = cudaSuccess;
+        if (s->traceSmem > 48 * 1024) {
+            e = cudaFuncSetAttribute(trace_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->traceSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->traceSmem);
+        }
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocksPerSM[0], trace_packed_kernel<false>, TRQ_BLOCK, s->traceSmem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocksPerSM[1], trace_packed_kernel<true>, TRQ_BLOCK, s->traceSmem);
+        if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel occupancy query failed: %s", cudaGetErrorString(e)));
+        if (s->blocksPerSM[0] < 1 || s->blocksPerSM[1] < 1)
+            return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->traceSmem));
+    }
 
     info.bytesReferenceLayout = (uint64_t)d->nSphere * sizeof(RefSphere) + (uint64_t)d->nSquare * sizeof(RefSquare) +
                                 (uint64_t)d->nCube * sizeof(RefCube) + (uint64_t)d->nVert * sizeof(RefVertex) +
@@ -494,10 +531,7 @@ int trq_host_sync(trq_scene* s) {
     if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_host_sync: NULL scene");
     DeviceGuard guard(s->device);
     std::lock_guard<std::mutex> lock(s->stageMutex);
-    if (!s->stageReady) return TRQ_OK;
-    TRQ_CUDA(cudaStreamSynchronize(s->sD2H));
-    TRQ_CUDA(cudaStreamSynchronize(s->sCompute));
-    return TRQ_OK;
+    return sync_staging(s);
 }
 
 int trq_expand_hits(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, uint32_t flags,
