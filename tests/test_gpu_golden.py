@@ -101,6 +101,47 @@ def test_streams_are_reentrant(c3):
         assert torch.equal(o, ref)
 
 
+def test_host_threads_are_reentrant(c3):
+    """SURVEY 8b threading row: one immutable scene, several host threads tracing at once -- device-pointer calls on
+    their own streams and host-pointer calls through the shared staging ring (ctypes drops the GIL inside the call)."""
+    import threading
+    torch = _torch()
+    from tracer_b200 import hits_to_numpy, rays_to_torch
+    prim, scene, rays = c3
+    sub = np.ascontiguousarray(rays[:700_000])
+    d = rays_to_torch(sub, "cuda:0")
+    want = hits_to_numpy(scene.hit(d)).view(np.uint8)
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def device_worker(k):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                outs = [scene.hit(d) for _ in range(6)]
+            st.synchronize()
+            results[k] = [hits_to_numpy(o).view(np.uint8) for o in outs]
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(e)
+
+    def host_worker(k):
+        try:
+            results[k] = [scene.hit(sub).view(np.uint8) for _ in range(3)]
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=device_worker, args=(k,)) for k in range(3)]
+    threads += [threading.Thread(target=host_worker, args=(k,)) for k in (3, 4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for k, outs in results.items():
+        for o in outs:
+            assert np.array_equal(o.reshape(-1), want.reshape(-1)), f"thread {k}"
+
+
 def test_sort_hint_changes_nothing_but_order_of_work(c3):
     """TRQ_SORT_RAYS reorders the work queue only: identical bytes out, for incoherent rays and for the degenerate
     batch whose rays all start at one point (one histogram bin)."""

@@ -9,7 +9,9 @@ timeout 900 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "
 timeout 400 python bench.py --impl reference > $O/bench_c3_reference.json 2> $O/bench_c3_reference.err
 timeout 400 python bench.py > $O/bench_c3.json 2> $O/bench_c3.err
 timeout 400 python bench.py --flush-l2 --no-cpu-baseline > $O/bench_c3_flushl2.json 2>> $O/bench_c3.err
-for w in c2 c4 soup1m; do timeout 400 python bench.py --workload $w --steps 100 > $O/bench_$w.json 2> $O/bench_$w.err; done
+for w in c1 c2 c3path c4 soup1m; do timeout 400 python bench.py --workload $w --steps 100 > $O/bench_$w.json 2> $O/bench_$w.err; done
+timeout 900 python bench.py --workload c5 --steps 10 --warmup 3 > $O/bench_c5.json 2> $O/bench_c5.err
+timeout 300 python tools/e2e_sweep.py > $O/e2e_sweep.txt 2>&1
 # every launch with its device time (cold-cache, serialised: compare SHARES)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_c3.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $O/ncu_list.log 2>&1

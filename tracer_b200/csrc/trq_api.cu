@@ -78,6 +78,9 @@ struct trq_scene {
     uint32_t stackDepth = 1;
     size_t traceSmem = 0;
     int blocksPerSM[2] = {0, 0};  // resident trace_packed_kernel CTAs per SM: [closest-hit, any-hit]
+    // stream-ordered scratch for TRQ_SORT_RAYS: a private pool that keeps its memory across synchronisations
+    // (the device's default pool hands it back at every sync and re-maps 64 MB on the next sorted launch)
+    cudaMemPool_t scratchPool = nullptr;
     // ray-queue heads
     unsigned long long* d_counters = nullptr;
     std::atomic<uint32_t> counterNext{0};
@@ -103,6 +106,7 @@ void free_scene(trq_scene* s) {
     cudaFree(s->d_verts); cudaFree(s->d_idx); cudaFree(s->d_bvh);
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph);
     cudaFree(s->d_counters);
+    if (s->scratchPool) cudaMemPoolDestroy(s->scratchPool);
     for (int b = 0; b < kStageBufs; ++b) {
         cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
         if (s->stageStream[b]) cudaStreamDestroy(s->stageStream[b]);
@@ -242,7 +246,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         uint32_t* scratch = nullptr;
         if (sortRays && n >= 65536) {
             const size_t words = (size_t)TRQ_SORT_BINS + 2 * (size_t)n;          // hist | keys | order
-            TRQ_CUDA(cudaMallocAsync((void**)&scratch, words * sizeof(uint32_t), st));
+            TRQ_CUDA(cudaMallocFromPoolAsync((void**)&scratch, words * sizeof(uint32_t), s->scratchPool, st));
             uint32_t* hist = scratch; uint32_t* keys = scratch + TRQ_SORT_BINS; uint32_t* order = keys + n;
             TRQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)TRQ_SORT_BINS * sizeof(uint32_t), st));
             const unsigned gb = (unsigned)((n + 255) / 256);
@@ -450,6 +454,17 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = N[0].bBOX.mini[k]; s->dev.rootMax[k] = N[0].bBOX.maxi[k]; }
     s->dev.nNode = d->nNode;
     s->stackDepth = info.maxDepth + 1;
+    {
+        cudaMemPoolProps pp = {};
+        pp.allocType = cudaMemAllocationTypePinned;
+        pp.handleTypes = cudaMemHandleTypeNone;
+        pp.location.type = cudaMemLocationTypeDevice;
+        pp.location.id = device;
+        cudaError_t e = cudaMemPoolCreate(&s->scratchPool, &pp);
+        unsigned long long keep = ~0ull;
+        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(s->scratchPool, cudaMemPoolAttrReleaseThreshold, &keep);
+        if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(e)));
+    }
     s->traceSmem = ((size_t)s->stackDepth + COLD_WORDS) * TRQ_BLOCK * sizeof(uint32_t);
     {
         cudaError_t e = cudaSuccess;
