@@ -333,7 +333,9 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, tr
         return (uint64_t)(v < 1024 ? 1024 : v);
     }();
     std::lock_guard<std::mutex> lock(s->stageMutex);
-    const uint64_t chunk = n < chunkRays ? n : chunkRays;
+    // a sorted chunk is only as coherent as it is large: C5 e2e 461 / 605 / 599 / 504 Mrays/s at 512K / 1M / 2M / 4M rays
+    const uint64_t want = (flags & TRQ_SORT_RAYS) ? 2 * chunkRays : chunkRays;
+    const uint64_t chunk = n < want ? n : want;
     int rc = ensure_staging(s, chunk);
     if (rc != TRQ_OK) return rc;
     uint64_t done = 0;
