@@ -182,6 +182,29 @@ int  trq_spawn_shadow(trq_scene* scene, const trq_ray* rays, const trq_hit* hits
                       uint64_t seedBase, uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex,
                       uint64_t* d_count, void* stream);
 
+/* ---- multi-GPU: hit gather through NVLink peer memory (one process per GPU, one node) -----------------------
+ * Rays shard across ranks with no collective. A consumer that wants EVERY rank's hits whole
+ * (the all-gather of trq_hit[N/R] of section 8e) gets them from the resolve kernel itself: each finished record is
+ * stored into slot [rank] of every rank's buffer over NVLink, then (count, step) are published with system-scope
+ * release stores -- no NCCL call, no second pass over the records.
+ *   1. every rank: trq_gather_create -> 64-byte handle; exchange the handles (any transport, e.g. MPI /
+ *      torch.distributed all_gather) into a world*64-byte array in rank order; trq_gather_connect.
+ *   2. per step: trq_trace_gather(rays of this rank) then trq_gather_wait -> hitsAll[r*capacity + i], counts[r];
+ *      both are asynchronous on `stream`; the buffers alternate between two parities, so the result of step k stays
+ *      valid until this rank calls trq_trace_gather for step k+2. Every rank must call both every step.
+ *   3. all ranks synchronise (barrier) before any of them calls trq_gather_destroy.
+ * trq_gather_status (after synchronising the stream) reports a peer that never published (timeout 10 s,
+ * TRQ_GATHER_TIMEOUT_MS) instead of hanging the GPU. */
+typedef struct trq_gather trq_gather;
+#define TRQ_GATHER_HANDLE_BYTES 64
+int  trq_gather_create(trq_scene* scene, uint32_t rank, uint32_t world, uint64_t capacity, trq_gather** out,
+                       void* handle /* TRQ_GATHER_HANDLE_BYTES */);
+int  trq_gather_connect(trq_gather* g, const void* handles /* world * TRQ_GATHER_HANDLE_BYTES, rank order */);
+int  trq_trace_gather(trq_scene* scene, trq_gather* g, const trq_ray* rays, uint64_t n, uint32_t flags, void* stream);
+int  trq_gather_wait(trq_gather* g, void* stream, const trq_hit** hitsAll, const uint64_t** counts);
+int  trq_gather_status(trq_gather* g);
+int  trq_gather_destroy(trq_gather* g);
+
 /* Per-kernel timing for roofline reports: when enabled, every device-pointer trq_trace records CUDA
  * events (on the caller's stream) around the traversal kernel and around the resolve kernel.
  * trq_profile_read waits for them and returns the SUMS over the launches since the last read

@@ -30,6 +30,9 @@ assert [p.shape[0] for p in parts] == [500, 501]
 whole = H.random_rays(n, seed=2)
 assert np.array_equal(torch.cat(parts).numpy().view(np.uint8), whole.view(np.float32).reshape(-1, 8).view(np.uint8))
 assert D.max_over_ranks(float(rank + 1)) == 2.0 and D.sum_over_ranks(float(hi - lo)) == float(n)
+# the handle exchange of the peer-memory gather (HitGather): rank order, any backend
+allh = D.exchange_handles(bytes([rank + 1]) * 64)
+assert allh == bytes([1]) * 64 + bytes([2]) * 64
 D.barrier()
 print("rank", rank, "ok")
 '''

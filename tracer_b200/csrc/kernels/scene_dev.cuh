@@ -64,4 +64,18 @@ struct CompactHit {
     uint32_t pad0, pad1;
 };
 
+// Peer-memory hit gather (trq_trace_gather): where the resolve kernel also writes every trq_hit, over NVLink, and
+// how it tells the peers that this rank's slot is complete.
+#define TRQ_GATHER_MAX_RANKS 16
+struct GatherDev {
+    trq_hit*            peerSlot[TRQ_GATHER_MAX_RANKS];    // slot [rank] of this step's buffer on every OTHER rank
+    unsigned long long* peerFlag[TRQ_GATHER_MAX_RANKS];    // flags[rank] on every other rank: last completed step
+    unsigned long long* peerCount[TRQ_GATHER_MAX_RANKS];   // counts[parity][rank] on every other rank
+    unsigned long long* ownFlag;                           // the same two words in this rank's own header
+    unsigned long long* ownCount;
+    uint32_t            nPeer;
+    unsigned int*       blocksDone;                        // local: CTAs of the resolve kernel that have finished
+    unsigned long long  step;
+};
+
 }  // namespace trq

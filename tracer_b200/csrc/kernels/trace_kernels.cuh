@@ -427,47 +427,98 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
 
 // ---------------------------------------------------------------------------------------------
 // compact -> trq_hit, in place. One thread per ray, fully coalesced.
+// GATHER: the resolved record is also stored into this rank's slot of every peer's buffer (NVLink peer memory, one
+// coalesced 1-KB run per warp and peer); the last CTA to finish publishes count and step number to every peer with
+// system-scope release stores, which the peers' gather_wait_kernel acquires.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool GATHER>
 __global__ void __launch_bounds__(256)
 resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n, const unsigned long long* __restrict__ nPtr,
-                    unsigned long long* queueHead) {
+                    unsigned long long* queueHead, const GatherDev G) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && queueHead) *queueHead = 0ull;        // the trace that used this queue head finished before this kernel started
-    if (i >= live_count(n, nPtr)) return;
-    float4* io = reinterpret_cast<float4*>(hits + i);
-    const float4 a = io[0], b = io[1];
-    trq_hit out;
-    out.t = 0.0f; out.pType = 0; out.pIndex = 0; out.leafNode = 0; out.u = 0.0f; out.v = 0.0f; out.material = 0; out.flags = 0;
-    if (__float_as_uint(b.y) != 0u) {
-        const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
-        const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
-        const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
-        const uint32_t leaf = __float_as_uint(a.y);
-        const int32_t pType = S.bvh[leaf].pType;
-        const uint32_t pIndex = S.bvh[leaf].pIndex;
-        out.t = a.x; out.pType = (uint32_t)pType; out.pIndex = pIndex; out.leafNode = leaf;
-        Surface s; s.front = 0; s.material = 0; s.uvx = s.uvy = 0.0f;
-        if (pType == TRQ_TRIANGLE) {
-            tri_surface(S.verts, S.idx, pIndex, a.z, a.w, ray, s);
-            out.u = a.z; out.v = a.w;
-        } else if (pType == TRQ_SPHERE) {
-            sphere_surface(&S.spheres[pIndex], a.x, ray, s);
-            out.u = s.uvx; out.v = s.uvy;
-        } else if (pType == TRQ_SQUARE) {
-            float t;
-            square_hit(&S.squares[pIndex], ray, a.x, a.x, t, &s);          // same t -> same a, b, uv
-            out.u = s.uvx; out.v = s.uvy;
-        } else if (pType == TRQ_CUBE) {
-            const uint32_t aux = __float_as_uint(b.x);
-            s.front = aux & 1u; s.material = aux >> 1;
-            out.u = a.z; out.v = a.w;
+    const uint64_t live = live_count(n, nPtr);
+    if (i < live) {
+        float4* io = reinterpret_cast<float4*>(hits + i);
+        const float4 a = io[0], b = io[1];
+        trq_hit out;
+        out.t = 0.0f; out.pType = 0; out.pIndex = 0; out.leafNode = 0; out.u = 0.0f; out.v = 0.0f; out.material = 0; out.flags = 0;
+        if (__float_as_uint(b.y) != 0u) {
+            const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
+            const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+            const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+            const uint32_t leaf = __float_as_uint(a.y);
+            const int32_t pType = S.bvh[leaf].pType;
+            const uint32_t pIndex = S.bvh[leaf].pIndex;
+            out.t = a.x; out.pType = (uint32_t)pType; out.pIndex = pIndex; out.leafNode = leaf;
+            Surface s; s.front = 0; s.material = 0; s.uvx = s.uvy = 0.0f;
+            if (pType == TRQ_TRIANGLE) {
+                tri_surface(S.verts, S.idx, pIndex, a.z, a.w, ray, s);
+                out.u = a.z; out.v = a.w;
+            } else if (pType == TRQ_SPHERE) {
+                sphere_surface(&S.spheres[pIndex], a.x, ray, s);
+                out.u = s.uvx; out.v = s.uvy;
+            } else if (pType == TRQ_SQUARE) {
+                float t;
+                square_hit(&S.squares[pIndex], ray, a.x, a.x, t, &s);          // same t -> same a, b, uv
+                out.u = s.uvx; out.v = s.uvy;
+            } else if (pType == TRQ_CUBE) {
+                const uint32_t aux = __float_as_uint(b.x);
+                s.front = aux & 1u; s.material = aux >> 1;
+                out.u = a.z; out.v = a.w;
+            }
+            out.material = s.material;
+            out.flags = TRQ_HIT_FLAG_HIT | (s.front ? TRQ_HIT_FLAG_FRONT : 0u);
         }
-        out.material = s.material;
-        out.flags = TRQ_HIT_FLAG_HIT | (s.front ? TRQ_HIT_FLAG_FRONT : 0u);
+        float4 o0, o1;
+        o0.x = out.t; o0.y = __uint_as_float(out.pType); o0.z = __uint_as_float(out.pIndex); o0.w = __uint_as_float(out.leafNode);
+        o1.x = out.u; o1.y = out.v; o1.z = __uint_as_float(out.material); o1.w = __uint_as_float(out.flags);
+        io[0] = o0; io[1] = o1;
+        if (GATHER) {
+#pragma unroll 1
+            for (uint32_t p = 0; p < G.nPeer; ++p) stg8(G.peerSlot[p] + i, o0, o1);
+        }
     }
-    float4 o0, o1;
-    o0.x = out.t; o0.y = __uint_as_float(out.pType); o0.z = __uint_as_float(out.pIndex); o0.w = __uint_as_float(out.leafNode);
-    o1.x = out.u; o1.y = out.v; o1.z = __uint_as_float(out.material); o1.w = __uint_as_float(out.flags);
-    io[0] = o0; io[1] = o1;
+    if (GATHER) {
+        __threadfence_system();                                   // this thread's peer stores before the CTA's arrival
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int prev = atomicAdd(G.blocksDone, 1u);
+            if (prev == gridDim.x - 1) {                          // last CTA: every record of this rank is on its way
+                *G.blocksDone = 0u;
+                __threadfence_system();
+                *G.ownCount = live;
+                st_release_sys(G.ownFlag, G.step);
+                for (uint32_t p = 0; p < G.nPeer; ++p) {
+                    *G.peerCount[p] = live;
+                    st_release_sys(G.peerFlag[p], G.step);
+                }
+            }
+        }
+    }
+}
+
+// Waits (on the stream) until every rank has published `step`; gives up after timeoutNs and raises *status.
+__global__ void gather_wait_kernel(const unsigned long long* flags, uint32_t world, unsigned long long step,
+                                   unsigned long long timeoutNs, volatile unsigned int* status) {
+    const uint32_t p = threadIdx.x;
+    if (p >= world) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(flags + p) < step) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeoutNs) { *status = 1u + p; break; }
+        __nanosleep(256);
+    }
 }
 
 // trq_hit -> HitRecord fields.

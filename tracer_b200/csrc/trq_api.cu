@@ -185,11 +185,11 @@ int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_i
 }
 
 int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, trq_hit* d_hits, cudaStream_t st,
-                 const unsigned long long* nPtr = nullptr) {
-    if (n == 0) return TRQ_OK;
+                 const unsigned long long* nPtr = nullptr, const GatherDev* gather = nullptr) {
+    if (n == 0 && !gather) return TRQ_OK;
     constexpr uint64_t kMaxPerLaunch = 1ull << 31;             // the kernels keep a 32-bit ray index per lane
     if (n > kMaxPerLaunch) {
-        if (nPtr) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect: capacity above 2^31 rays");
+        if (nPtr || gather) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect / trq_trace_gather: more than 2^31 rays");
         for (uint64_t off = 0; off < n; off += kMaxPerLaunch) {
             const uint64_t m = (n - off) < kMaxPerLaunch ? (n - off) : kMaxPerLaunch;
             const int rc = launch_trace(s, d_rays + off, m, flags, d_hits + off, st);
@@ -204,7 +204,9 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         prof = s->evProf[s->profHead % kProfRing];
         s->profHead++; if (s->profCount < kProfRing) s->profCount++;
     }
-    if (flags & TRQ_KERNEL_REFLAYOUT) {
+    if (n == 0) {
+        // gather with an empty batch: nothing to trace, but the peers still wait for this rank's step
+    } else if (flags & TRQ_KERNEL_REFLAYOUT) {
         const unsigned block = 128;
         const uint64_t grid = (n + block - 1) / block;
         if (grid > 0x7fffffffull) return trq::fail(TRQ_ERR_INVALID, "trq_trace: batch too large");
@@ -264,8 +266,9 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
     {
         const unsigned block = 256;
-        const uint64_t grid = (n + block - 1) / block;
-        resolve_hits_kernel<<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr, usedCounter);
+        const uint64_t grid = n ? (n + block - 1) / block : 1;
+        if (gather) resolve_hits_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr, usedCounter, *gather);
+        else        resolve_hits_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr, usedCounter, GatherDev{});
         g_launches++;
     }
     if (prof) TRQ_CUDA(cudaEventRecord(prof[2], st));
@@ -667,6 +670,146 @@ int trq_spawn_shadow(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uin
                                                                       (unsigned long long*)d_count);
     g_launches++;
     TRQ_CUDA(cudaGetLastError());
+    return TRQ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
+// Peer-memory hit gather (a consumer that wants every rank's hits whole). One process per GPU;
+// every rank owns a buffer [parity][rank][capacity] of trq_hit plus a small header (flags, counts), exported through
+// CUDA IPC. trq_trace_gather traces this rank's rays and its resolve kernel stores each finished record into slot
+// [rank] of EVERY rank's buffer over NVLink -- the all-gather is fused into the kernel that produces the records, no
+// NCCL call and no second pass over the data -- then publishes (count, step) with system-scope release stores.
+// trq_gather_wait enqueues a small kernel that acquires all ranks' step numbers. Two parities: a rank can run one
+// step ahead of a peer that is still consuming the previous one, never two (it would need the peer's next flag).
+namespace {
+constexpr size_t kGatherHeader = 4096;                 // flags[16] u64 @0, counts[2][16] u64 @128, blocksDone u32 @2048
+constexpr size_t kGatherCountsAt = 128, kGatherBlocksDoneAt = 2048;
+}
+
+struct trq_gather {
+    trq_scene* scene = nullptr;
+    uint32_t rank = 0, world = 1;
+    uint64_t capacity = 0;
+    uint8_t* base = nullptr;
+    uint8_t* peerBase[TRQ_GATHER_MAX_RANKS] = {};
+    unsigned int* h_status = nullptr;                  // pinned + mapped: raised by gather_wait_kernel on timeout
+    unsigned int* d_status = nullptr;
+    unsigned long long step = 0;
+    bool connected = false;
+    size_t slot_offset(unsigned parity, uint32_t r) const {
+        return kGatherHeader + ((size_t)parity * world + r) * capacity * sizeof(trq_hit);
+    }
+};
+
+extern "C" {
+
+int trq_gather_create(trq_scene* s, uint32_t rank, uint32_t world, uint64_t capacity, trq_gather** out, void* handle) {
+    if (!s || !out || !handle) return trq::fail(TRQ_ERR_INVALID, "trq_gather_create: NULL argument");
+    *out = nullptr;
+    if (world == 0 || world > TRQ_GATHER_MAX_RANKS || rank >= world)
+        return trq::fail(TRQ_ERR_INVALID, "trq_gather_create: rank %u / world %u (at most %d ranks)", rank, world, TRQ_GATHER_MAX_RANKS);
+    if (capacity == 0 || capacity > (1ull << 31)) return trq::fail(TRQ_ERR_INVALID, "trq_gather_create: capacity out of range");
+    static_assert(sizeof(cudaIpcMemHandle_t) == TRQ_GATHER_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    trq_gather* g = new (std::nothrow) trq_gather();
+    if (!g) return trq::fail(TRQ_ERR_NOMEM, "trq_gather_create: out of host memory");
+    g->scene = s; g->rank = rank; g->world = world; g->capacity = capacity;
+    const size_t total = kGatherHeader + 2 * (size_t)world * capacity * sizeof(trq_hit);
+    cudaError_t e = cudaMalloc((void**)&g->base, total);
+    if (e == cudaSuccess) e = cudaMemset(g->base, 0, kGatherHeader);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&g->h_status, sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) { *g->h_status = 0; e = cudaHostGetDevicePointer((void**)&g->d_status, g->h_status, 0); }
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, g->base);
+    if (e != cudaSuccess) {
+        cudaFree(g->base); if (g->h_status) cudaFreeHost(g->h_status); delete g;
+        return trq::fail(TRQ_ERR_CUDA, "trq_gather_create (%zu bytes): %s", total, cudaGetErrorString(e));
+    }
+    memcpy(handle, &h, sizeof h);
+    *out = g;
+    return TRQ_OK;
+}
+
+int trq_gather_connect(trq_gather* g, const void* handles) {
+    if (!g || (!handles && g->world > 1)) return trq::fail(TRQ_ERR_INVALID, "trq_gather_connect: NULL argument");
+    if (g->connected) return trq::fail(TRQ_ERR_INVALID, "trq_gather_connect: already connected");
+    DeviceGuard guard(g->scene->device);
+    for (uint32_t r = 0; r < g->world; ++r) {
+        if (r == g->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t*)handles + (size_t)r * sizeof h, sizeof h);
+        cudaError_t e = cudaIpcOpenMemHandle((void**)&g->peerBase[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return trq::fail(TRQ_ERR_CUDA, "trq_gather_connect: cudaIpcOpenMemHandle(rank %u) failed: %s (one process per GPU, same node)",
+                             r, cudaGetErrorString(e));
+    }
+    g->connected = true;
+    return TRQ_OK;
+}
+
+int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t n, uint32_t flags, void* stream) {
+    if (!s || !g || g->scene != s) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: NULL or foreign scene / gather");
+    if (!g->connected) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: call trq_gather_connect first");
+    if (flags & (TRQ_HOST_PTRS | TRQ_HOST_ASYNC)) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: device pointers only");
+    if (n > g->capacity) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: %llu rays exceed the capacity %llu", (unsigned long long)n, (unsigned long long)g->capacity);
+    if (n && !rays) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: NULL rays");
+    if (((uintptr_t)rays) & 31u) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: rays must be 32-byte aligned");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    const unsigned long long step = ++g->step;
+    const unsigned parity = (unsigned)(step & 1ull);
+    GatherDev G{};
+    G.step = step;
+    G.blocksDone = (unsigned int*)(g->base + kGatherBlocksDoneAt);
+    G.ownFlag = (unsigned long long*)g->base + g->rank;
+    G.ownCount = (unsigned long long*)(g->base + kGatherCountsAt) + parity * TRQ_GATHER_MAX_RANKS + g->rank;
+    for (uint32_t r = 0; r < g->world; ++r) {
+        if (r == g->rank) continue;
+        const uint32_t k = G.nPeer++;
+        G.peerSlot[k] = (trq_hit*)(g->peerBase[r] + g->slot_offset(parity, g->rank));
+        G.peerFlag[k] = (unsigned long long*)g->peerBase[r] + g->rank;
+        G.peerCount[k] = (unsigned long long*)(g->peerBase[r] + kGatherCountsAt) + parity * TRQ_GATHER_MAX_RANKS + g->rank;
+    }
+    trq_hit* own = (trq_hit*)(g->base + g->slot_offset(parity, g->rank));
+    return launch_trace(s, rays, n, flags, own, (cudaStream_t)stream, nullptr, &G);
+}
+
+int trq_gather_wait(trq_gather* g, void* stream, const trq_hit** hitsAll, const uint64_t** counts) {
+    if (!g) return trq::fail(TRQ_ERR_INVALID, "trq_gather_wait: NULL gather");
+    if (g->step == 0) return trq::fail(TRQ_ERR_INVALID, "trq_gather_wait: nothing traced yet");
+    DeviceGuard guard(g->scene->device);
+    static const unsigned long long timeoutNs = [] {
+        const char* e = getenv("TRQ_GATHER_TIMEOUT_MS");
+        return (unsigned long long)(e ? atoll(e) : 10000) * 1000000ull;
+    }();
+    gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)g->base, g->world, g->step, timeoutNs, g->d_status);
+    g_launches++;
+    TRQ_CUDA(cudaGetLastError());
+    const unsigned parity = (unsigned)(g->step & 1ull);
+    if (hitsAll) *hitsAll = (const trq_hit*)(g->base + g->slot_offset(parity, 0));
+    if (counts) *counts = (const uint64_t*)(g->base + kGatherCountsAt) + parity * TRQ_GATHER_MAX_RANKS;
+    return TRQ_OK;
+}
+
+int trq_gather_status(trq_gather* g) {
+    if (!g) return trq::fail(TRQ_ERR_INVALID, "trq_gather_status: NULL gather");
+    const unsigned int v = *(volatile unsigned int*)g->h_status;
+    if (v) return trq::fail(TRQ_ERR_CUDA, "trq_gather_wait: rank %u did not publish its hits before the timeout", v - 1);
+    return TRQ_OK;
+}
+
+int trq_gather_destroy(trq_gather* g) {
+    if (!g) return TRQ_OK;
+    DeviceGuard guard(g->scene->device);
+    cudaDeviceSynchronize();
+    for (uint32_t r = 0; r < g->world; ++r) if (g->peerBase[r]) cudaIpcCloseMemHandle(g->peerBase[r]);
+    cudaFree(g->base);
+    if (g->h_status) cudaFreeHost(g->h_status);
+    delete g;
     return TRQ_OK;
 }
 

@@ -4,7 +4,9 @@ The path shards by ray batch: the scene is read-only and 
 independent, so there is NO collective on the data path. The only communication is
   * once per scene: broadcast of the six reference-layout arrays from rank 0 (NCCL over NVLink when the
     backend is nccl; gloo on CPU for the tests), after which every rank calls trq_scene_create;
-  * optionally, after tracing: all-gather of the 32-byte hit records for a consumer that wants them whole.
+  * optionally, after tracing: all-gather of the 32-byte hit records for a consumer that wants them whole --
+    either NCCL (gather_hits / trace_and_gather) or, fused into the kernel that produces the records, stores into
+    every rank's buffer over NVLink peer memory (HitGather -> trq_trace_gather).
 """
 import os
 
@@ -170,3 +172,77 @@ def trace_and_gather(scene, rays, hits_local, hits_all, any=False, sort=False, c
         w.wait()
     torch.cuda.current_stream(rays.device).wait_stream(comm_stream)
     return works[-1] if works else None
+
+
+def exchange_handles(handle):
+    """All ranks contribute a bytes object; returns their concatenation in rank order (any backend)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return bytes(handle)
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, bytes(handle))
+    if any(len(p) != len(handle) for p in parts):
+        raise RuntimeError("exchange_handles: ranks contributed handles of different sizes")
+    return b"".join(parts)
+
+
+class _DevArray:
+    """Raw device memory as a CUDA array for torch.as_tensor (no copy)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+class HitGather:
+    """Hit all-gather fused into the resolve kernel (trq_trace_gather): every rank's records land in every rank's
+    (world, capacity, 8) buffer through NVLink peer stores. One process per GPU on one node.
+
+        g = HitGather(scene, capacity)          # collective: allocates, exchanges CUDA-IPC handles, connects
+        g.trace(rays); hits_all, counts = g.wait()      # every rank, every step; hits_all[r, :counts[r]]
+        g.close()                               # collective (barrier inside)
+    """
+
+    def __init__(self, scene, capacity):
+        import ctypes as C
+        from ._lib import lib
+        from ._lib import check
+        rank, _, world = env_world()
+        import torch.distributed as dist
+        if dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        self.scene, self.rank, self.world, self.capacity = scene, rank, world, int(capacity)
+        self._lib, self._check = lib, check
+        self._h = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        check(lib.trq_gather_create(scene._h, rank, world, self.capacity, C.byref(self._h), handle), "trq_gather_create")
+        allh = exchange_handles(handle.raw)
+        check(lib.trq_gather_connect(self._h, allh), "trq_gather_connect")
+        barrier()
+
+    def trace(self, rays, any=False, sort=False, stream=None):
+        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
+        self._check(self._lib.trq_trace_gather(self.scene._h, self._h, rays.data_ptr(), rays.shape[0], flags, self.scene._stream(stream)),
+                    "trq_trace_gather")
+
+    def wait(self, stream=None):
+        """Enqueues the wait for every rank's records of the last trace(); returns ((world, capacity, 8) float32 view of the
+        local buffer, (world,) int64 view of the per-rank counts). Both are valid until the next-but-one trace()."""
+        import ctypes as C
+        import torch
+        hp, cp = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.trq_gather_wait(self._h, self.scene._stream(stream), C.byref(hp), C.byref(cp)), "trq_gather_wait")
+        dev = torch.device("cuda", self.scene.device)
+        hits = torch.as_tensor(_DevArray(hp.value, (self.world, self.capacity, 8), "<f4"), device=dev)
+        counts = torch.as_tensor(_DevArray(cp.value, (self.world,), "<i8"), device=dev)
+        return hits, counts
+
+    def status(self):
+        self._check(self._lib.trq_gather_status(self._h), "trq_gather_status")
+
+    def close(self):
+        if self._h:
+            import torch
+            torch.cuda.synchronize(self.scene.device)
+            barrier()
+            self._lib.trq_gather_destroy(self._h)
+            self._h = None
