@@ -460,30 +460,38 @@ def run_gpu_arm(a):
         del g_all, g_local
         # the same result through trq_trace_gather: the resolve kernel stores every record into every rank's buffer
         # over NVLink peer memory and publishes (count, step); no NCCL on the data path
-        hg = D.HitGather(scene, n_common)
-        for _ in range(3):
-            hg.trace(g_rays, any=any_hit, sort=sort); hg.wait()
-        D.barrier(); torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(g_steps):
-            hg.trace(g_rays, any=any_hit, sort=sort)
-            p_all, p_counts = hg.wait()
-        e1.record(); torch.cuda.synchronize()
-        hg.status()
-        p_ms = D.max_over_ranks(e0.elapsed_time(e1))
-        others = [r for r in range(world) if r != rank]
-        full = bool((p_counts == n_common).all()) and bool(torch.equal(p_all[rank].view(torch.int32), d_hits[:n_common].view(torch.int32)))
-        # slot r must hold rank r's records: compare a slice with an NCCL gather of the same slice
-        m = min(n_common, 1 << 18)
-        ref = D.gather_hits(d_hits[:m].contiguous())
-        full = full and all(bool(torch.equal(p_all[r, :m].view(torch.int32), ref[r].view(torch.int32))) for r in others)
-        full = bool(-D.max_over_ranks(-float(full)) == 1.0)
-        with_gather = {"value": round(n_common * world * g_steps / p_ms / 1e3, 2), "unit": UNIT, "steps": g_steps,
-                       "ms_per_step": round(p_ms / g_steps, 4), "gathered_bytes_per_rank_per_step": int(n_common * world * 32),
-                       "how": "trq_trace_gather: all-gather fused into the resolve kernel (peer stores over NVLink + release/acquire flags)",
-                       "all_slots_match": full, "nccl_overlapped": nccl}
-        hg.close()
+        try:
+            hg = D.HitGather(scene, n_common)
+            for _ in range(3):
+                hg.trace(g_rays, any=any_hit, sort=sort); hg.wait()
+            D.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(g_steps):
+                hg.trace(g_rays, any=any_hit, sort=sort)
+                p_all, p_counts = hg.wait()
+            e1.record(); torch.cuda.synchronize()
+            published = True
+            try:
+                hg.status()
+            except RuntimeError:                                  # a peer never published: reported, and no rank leaves the collectives below
+                published = False
+            p_ms = D.max_over_ranks(e0.elapsed_time(e1))
+            others = [r for r in range(world) if r != rank]
+            full = published and bool((p_counts == n_common).all()) and bool(torch.equal(p_all[rank].view(torch.int32), d_hits[:n_common].view(torch.int32)))
+            # slot r must hold rank r's records: compare a slice with an NCCL gather of the same slice
+            m = min(n_common, 1 << 18)
+            ref = D.gather_hits(d_hits[:m].contiguous())
+            full = full and all(bool(torch.equal(p_all[r, :m].view(torch.int32), ref[r].view(torch.int32))) for r in others)
+            full = bool(-D.max_over_ranks(-float(full)) == 1.0)
+            with_gather = {"value": round(n_common * world * g_steps / p_ms / 1e3, 2), "unit": UNIT, "steps": g_steps,
+                           "ms_per_step": round(p_ms / g_steps, 4), "gathered_bytes_per_rank_per_step": int(n_common * world * 32),
+                           "how": "trq_trace_gather: all-gather fused into the resolve kernel (peer stores over NVLink + release/acquire flags)",
+                           "all_slots_match": full, "nccl_overlapped": nccl}
+            hg.close()
+        except RuntimeError as e:                                 # raised on every rank alike (HitGather agrees on failures)
+            with_gather = dict(nccl, unit=UNIT, steps=g_steps, gathered_bytes_per_rank_per_step=int(n_common * world * 32),
+                               peer_gather_error=str(e))
 
     # ---- multi-GPU: scene checksum agreement + gathered hit count (not timed)
     gathered = None

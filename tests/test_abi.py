@@ -98,3 +98,18 @@ def test_product_does_not_import_the_oracle():
                     src = open(os.path.join(dirpath, f), errors="replace").read()
                     for needle in ("from oracle", "import oracle", "pyoracle", "liboracle", "libtracer_ref", "oracle_rq.h", "orq_"):
                         assert needle not in src, f"{dirpath}/{f} references the oracle ({needle})"
+
+
+def test_gather_argument_validation_needs_no_gpu(built):
+    """The peer-memory gather refuses bad arguments with a status and a message (no exception, no crash)."""
+    import ctypes as C
+    from tracer_b200._lib import lib
+    g = C.c_void_p()
+    handle = C.create_string_buffer(64)
+    assert lib.trq_gather_create(None, 0, 2, 1000, C.byref(g), handle) != 0
+    assert b"NULL" in lib.trq_last_error_string()
+    assert lib.trq_gather_connect(None, None) != 0
+    assert lib.trq_trace_gather(None, None, None, 0, 0, None) != 0
+    assert lib.trq_gather_wait(None, None, None, None) != 0
+    assert lib.trq_gather_status(None) != 0
+    assert lib.trq_gather_destroy(None) == 0

@@ -214,10 +214,21 @@ class HitGather:
         self._lib, self._check = lib, check
         self._h = C.c_void_p()
         handle = C.create_string_buffer(64)
-        check(lib.trq_gather_create(scene._h, rank, world, self.capacity, C.byref(self._h), handle), "trq_gather_create")
+        # every step below is collective: a rank that fails must not leave the others waiting, so the outcome of each
+        # local call is agreed on (max over ranks) before anyone proceeds or raises
+        rc = lib.trq_gather_create(scene._h, rank, world, self.capacity, C.byref(self._h), handle)
+        self._agree(rc, "trq_gather_create")
         allh = exchange_handles(handle.raw)
-        check(lib.trq_gather_connect(self._h, allh), "trq_gather_connect")
-        barrier()
+        rc = lib.trq_gather_connect(self._h, allh)
+        self._agree(rc, "trq_gather_connect")
+
+    def _agree(self, rc, what):
+        msg = self._lib.trq_last_error_string().decode() if rc != 0 else ""
+        if max_over_ranks(float(rc != 0)) != 0.0:
+            if self._h:
+                self._lib.trq_gather_destroy(self._h)
+                self._h = None
+            raise RuntimeError(f"{what} failed on {'this rank: ' + msg if rc != 0 else 'another rank'}")
 
     def trace(self, rays, any=False, sort=False, stream=None):
         flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
