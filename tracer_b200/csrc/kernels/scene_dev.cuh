@@ -59,9 +59,9 @@ struct CompactHit {
     float    t;
     uint32_t leafNode;   // bvhList index of the winning leaf
     float    u, v;       // triangle barycentrics / cube uv captured at hit time
-    uint32_t aux;        // cube: front | material << 1
+    uint32_t aux;        // cube / square: front | material << 1; every other hit: bits of ray direction x
     uint32_t hit;        // 0 / 1
-    uint32_t pad0, pad1;
+    float    dy, dz;     // ray direction y, z (triangle front-face test in resolve_hits without re-reading the ray)
 };
 
 // Peer-memory hit gather (trq_trace_gather): where the resolve kernel also writes every trq_hit, over NVLink, and

@@ -47,8 +47,10 @@ __device__ __forceinline__ void stg8(void* p, const float4& a, const float4& b) 
                  :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
 }
 
+// aux: cube hits = front | material << 1; every other hit = bits of the ray direction's x, with y and z in dy / dz,
+// so that resolve_hits_kernel can do a triangle's front-face test without reading the ray again.
 __device__ __forceinline__ void store_compact(trq_hit* hits, uint64_t i, bool hit, float t, uint32_t leaf,
-                                              float u, float v, uint32_t aux) {
+                                              float u, float v, uint32_t aux, float dy = 0.0f, float dz = 0.0f) {
     float4 a, b;
     a.x = hit ? t : 0.0f;
     a.y = __uint_as_float(hit ? leaf : 0u);
@@ -56,7 +58,7 @@ __device__ __forceinline__ void store_compact(trq_hit* hits, uint64_t i, bool hi
     a.w = hit ? v : 0.0f;
     b.x = __uint_as_float(hit ? aux : 0u);
     b.y = __uint_as_float(hit ? 1u : 0u);
-    b.z = 0.0f; b.w = 0.0f;
+    b.z = dy; b.w = dz;
     stg8(hits + i, a, b);
 }
 
@@ -136,13 +138,16 @@ trace_reflayout_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* __
                                      ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, range_y, &o4);
                 if (h) { t = o4.x; u = o4.y; v = o4.z; a = __float_as_uint(o4.w); }
             }
-            if (h) { range_y = t; best = sel; bu = u; bv = v; aux = a; }
+            if (h) {                                                      // aux word: cube front/material, else d.x (see store_compact)
+                range_y = t; best = sel; bu = u; bv = v;
+                aux = (pType == TRQ_SQUARE || pType == TRQ_CUBE) ? a : __float_as_uint(ray.d.x);
+            }
             if (ANY && range_y < test_t) { done_any = true; break; }      // :244
             tested_index = sel;                                           // :246
         } while (tested_index != 0);                                      // :248
     }
     const bool hit = done_any || (range_y < test_t);                      // :251
-    store_compact(hits, i, hit && best != 0xffffffffu, range_y, best, bu, bv, aux);
+    store_compact(hits, i, hit && best != 0xffffffffu, range_y, best, bu, bv, aux, ray.d.y, ray.d.z);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -292,8 +297,11 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         if (pending) {
             const uint32_t best = cold[COLD_BEST * TRQ_BLOCK];
             const bool hit = (range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) && best != 0xffffffffu;   // Render.hh:251
+            // triangle / sphere hits carry the ray direction (aux word = d.x) so that resolve_hits_kernel does not
+            // have to read the ray again for the front-face test
             store_compact(P.hits, cold[COLD_RAY * TRQ_BLOCK], hit, range_y, best,
-                          coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK]);
+                          coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK],
+                          coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
             pending = false;
         }
     };
@@ -415,7 +423,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     range_y = t;
                     cold[COLD_BEST * TRQ_BLOCK] = leaf;
                     coldf[COLD_U * TRQ_BLOCK] = u; coldf[COLD_V * TRQ_BLOCK] = v;
-                    cold[COLD_AUX * TRQ_BLOCK] = a;
+                    cold[COLD_AUX * TRQ_BLOCK] = (kind == REF_SQUARE || kind == REF_CUBE) ? a : __float_as_uint(ray.d.x);
                 }
                 if (ANY && range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) cur = TRQ_REF_DONE_WORD;   // :244
                 else pop();
@@ -452,12 +460,17 @@ resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits,
         trq_hit out;
         out.t = 0.0f; out.pType = 0; out.pIndex = 0; out.leafNode = 0; out.u = 0.0f; out.v = 0.0f; out.material = 0; out.flags = 0;
         if (__float_as_uint(b.y) != 0u) {
-            const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
-            const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
-            const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
             const uint32_t leaf = __float_as_uint(a.y);
             const int32_t pType = S.bvh[leaf].pType;
             const uint32_t pIndex = S.bvh[leaf].pIndex;
+            RayCtx ray;
+            if (pType == TRQ_TRIANGLE) {                          // only the direction matters (checkFace), and the trace kernel left it here
+                ray = make_ray_ctx(0.0f, 0.0f, 0.0f, b.x, b.z, b.w);
+            } else {
+                const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
+                const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+                ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+            }
             out.t = a.x; out.pType = (uint32_t)pType; out.pIndex = pIndex; out.leafNode = leaf;
             Surface s; s.front = 0; s.material = 0; s.uvx = s.uvy = 0.0f;
             if (pType == TRQ_TRIANGLE) {
