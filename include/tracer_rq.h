@@ -182,6 +182,19 @@ int  trq_spawn_shadow(trq_scene* scene, const trq_ray* rays, const trq_hit* hits
                       uint64_t seedBase, uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex,
                       uint64_t* d_count, void* stream);
 
+/* The two spawns drawing from the reference's per-pixel RNG state texture (row f-4: RGBA32Uint, 4 x uint32 per pixel =
+ * {state >> 32, state, inc >> 32, inc}; toRNG / exRNG, Render.hh:96-120; loaded at kernel entry and stored back at exit,
+ * Render.metal:511-557). Ray i belongs to pixel pixelOf[i] (NULL: i); its PCG32 stream is loaded from
+ * rngState[4 * pixel], advanced by the draws and stored back, so the next bounce / the next frame continues it.
+ * srcIndex[k] receives the PIXEL of output ray k: pass it as pixelOf of the next wave. rngState == NULL behaves like the
+ * calls above (PCG32(seedBase + i, 1)). Two rays of one batch must not share a pixel. */
+int  trq_spawn_bounce_rng(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n,
+                          uint64_t seedBase, const uint32_t* pixelOf, uint32_t* rngState, trq_ray* out, uint32_t* srcIndex,
+                          uint64_t* d_count, void* stream);
+int  trq_spawn_shadow_rng(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n,
+                          uint64_t seedBase, const uint32_t* pixelOf, uint32_t* rngState, uint32_t lightA, uint32_t lightB,
+                          trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream);
+
 /* ---- multi-GPU: hit gather through NVLink peer memory (one process per GPU, one node) -----------------------
  * Rays shard across ranks with no collective. A consumer that wants EVERY rank's hits whole
  * (the all-gather of trq_hit[N/R] of section 8e) gets them from the resolve kernel itself: each finished record is

@@ -211,6 +211,20 @@ class Reference:
         self.lib.ref_cosine_sample_hemisphere(C.c_void_p(u.ctypes.data), C.c_void_p(out.ctypes.data))
         return out
 
+    def to_rng(self, rgba):
+        """toRNG (Render.hh:96-107): 4 x uint32 texel -> (inc, state)."""
+        t = np.ascontiguousarray(rgba, dtype=np.uint32)
+        out = np.zeros(2, dtype=np.uint64)
+        self.lib.ref_to_rng(C.c_void_p(t.ctypes.data), C.c_void_p(out.ctypes.data))
+        return int(out[0]), int(out[1])
+
+    def ex_rng(self, inc, state):
+        """exRNG (Render.hh:109-120): (inc, state) -> 4 x uint32 texel."""
+        a = np.array([inc, state], dtype=np.uint64)
+        out = np.zeros(4, dtype=np.uint32)
+        self.lib.ref_ex_rng(C.c_void_p(a.ctypes.data), C.c_void_p(out.ctypes.data))
+        return out
+
 
 NEXTWEEK_PATH = os.path.join(_HERE, "libnextweek_bvh.so")
 

@@ -264,4 +264,16 @@ void ref_cosine_sample_hemisphere(const float* u, float* out) {
 float ref_next_float_up(float v) { return NextFloatUp(v); }
 float ref_next_float_down(float v) { return NextFloatDown(v); }
 
+// the per-pixel RNG state texture <-> pcg32_t (Render.hh:96-120); out / in = {inc, state}
+void ref_to_rng(const uint32_t* rgba, uint64_t* inc_state) {
+    vec<uint32_t, 4> c; c.r = rgba[0]; c.g = rgba[1]; c.b = rgba[2]; c.a = rgba[3];
+    pcg32_t r = toRNG(c);
+    inc_state[0] = r.inc; inc_state[1] = r.state;
+}
+void ref_ex_rng(const uint64_t* inc_state, uint32_t* rgba) {
+    pcg32_t r = { inc_state[0], inc_state[1] };
+    vec<uint32_t, 4> c = exRNG(r);
+    rgba[0] = c.r; rgba[1] = c.g; rgba[2] = c.b; rgba[3] = c.a;
+}
+
 }  // extern "C"

@@ -102,3 +102,48 @@ def test_device_wavefront_two_bounces(cornell, port):
     scene.hit_indirect(r1[:64].contiguous(), zero, out=sentinel)
     torch.cuda.synchronize()
     assert bool((sentinel == 7.0).all())
+
+
+def test_rng_state_texture_two_waves(cornell):
+    """Row f-4: the device spawns draw from and advance the reference's per-pixel RNG texture (Render.hh:96-120),
+    wave after wave, exactly like the host restatement: state bytes identical, same rays, srcIndex = pixel."""
+    torch = _torch()
+    from tracer_b200 import harness as H
+    prim, scene = cornell
+    W, Hh = 320, 180
+    d = scene.cast_rays((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)), W, Hh)
+    hits = scene.hit(d)
+    rng = np.random.default_rng(9)
+    tex0 = rng.integers(0, 1 << 32, size=(W * Hh, 4), dtype=np.uint64).astype(np.uint32)
+    tex_d = torch.from_numpy(tex0.view(np.int32)).to("cuda:0")
+    tex_h = tex0.copy()
+    # wave 1: bounce rays of the primary hits
+    r1, s1, c1 = scene.spawn_bounce(d, hits, rng_state=tex_d)
+    recs0 = scene.expand(d, hits).cpu().numpy().view(L.record_dtype).reshape(-1)
+    w1, ws1 = H.bounce_rays(recs0, rng_state=tex_h)
+    n1 = int(c1.item())
+    assert n1 == w1.size
+    assert np.array_equal(tex_d.cpu().numpy().view(np.uint32), tex_h), "RNG texture after wave 1"
+    src1 = s1.cpu().numpy()[:n1].astype(np.uint32)
+    order = np.argsort(src1, kind="stable")
+    assert np.array_equal(src1[order], ws1)
+    g1 = _np_rays(r1, n1)[order]
+    assert np.array_equal(bits(g1["o"]), bits(w1["o"]))
+    err = np.abs(g1["d"].astype(np.float64) - w1["d"].astype(np.float64)).max(axis=1)
+    assert np.quantile(err, 0.99) < 2e-6 and err.max() < 2e-3
+    # wave 2: shadow rays of the bounce hits, routed to their pixels through pixel_of = srcIndex of wave 1
+    h1 = scene.hit_indirect(r1, c1)
+    sh, s2, c2 = scene.spawn_shadow(r1, h1, 5, 6, count_in=c1, pixel_of=s1, rng_state=tex_d)
+    n2 = int(c2.item())
+    r1_np = _np_rays(r1, n1).copy()
+    recs1 = scene.expand(r1_np, np.ascontiguousarray(h1.cpu().numpy().view(L.hit_dtype).reshape(-1)[:n1]))
+    w2, ws2 = H.shadow_rays(recs1, prim.squareList[5:6], prim.squareList[6:7], pixel_of=src1, rng_state=tex_h)
+    assert n2 == w2.size and 0 < n2 < n1
+    assert np.array_equal(tex_d.cpu().numpy().view(np.uint32), tex_h), "RNG texture after wave 2"
+    src2 = s2.cpu().numpy()[:n2].astype(np.uint32)
+    order2 = np.argsort(src2, kind="stable")
+    assert np.array_equal(src2[order2], np.sort(ws2))                   # pixels, not ray indices
+    g2 = _np_rays(sh, n2)[order2]
+    w2s = w2[np.argsort(ws2, kind="stable")]
+    assert np.array_equal(bits(g2["o"]), bits(w2s["o"])) and np.array_equal(bits(g2["d"]), bits(w2s["d"]))
+    assert (tex_h != tex0).any(axis=1).sum() == n1                      # exactly the pixels that hit drew numbers

@@ -72,3 +72,57 @@ def test_subdivide_and_scene_sizes():
     assert len(t2) == 32 and len(p2) == 25                                       # shared edge midpoints
     c2 = H.scene_c2()
     assert c2.nTri == 14 + 24 + 15704
+
+
+_M64 = (1 << 64) - 1
+_MULT = 6364136223846793005
+
+
+def _pcg_step(state, inc):
+    return (state * _MULT + inc) & _M64
+
+
+def _pcg_seeded(seed, seq):
+    """pcg32_srandom_r (pcg_basic.c:44-51): -> (state, inc)."""
+    inc = ((seq << 1) | 1) & _M64
+    state = _pcg_step(0, inc)
+    state = (state + seed) & _M64
+    return _pcg_step(state, inc), inc
+
+
+def test_rng_state_texture_is_the_references_wire_format(reference):
+    """Row f-4: the spawns draw from / write back the per-pixel RNG texture exactly as Render.metal:511-557 does
+    (toRNG / exRNG, Render.hh:96-120, executed from the verbatim build)."""
+    prim = H.scene_reference_cornell()
+    first = reference.trace(prim, H.cornell_camera_rays(48, 27))
+    n = first.size
+    hit = first["hit"] == 1
+    rng = np.random.default_rng(5)
+    tex0 = rng.integers(0, 1 << 32, size=(n, 4), dtype=np.uint64).astype(np.uint32)
+    tex = tex0.copy()
+    rays, src = H.bounce_rays(first, rng_state=tex)
+    assert np.array_equal(tex[~hit], tex0[~hit])                       # a pixel that spawns nothing draws nothing
+    for i in np.nonzero(hit)[0][::29]:
+        inc, state = reference.to_rng(tex0[i])
+        state = _pcg_step(_pcg_step(state, inc), inc)                  # sample2D = two draws
+        assert np.array_equal(tex[i], reference.ex_rng(inc, state)), i
+    # a texture that holds the streams PCG32(seedBase + i, 1) reproduces the seeded producer bit for bit
+    seeded = np.zeros((n, 4), dtype=np.uint32)
+    for i in range(n):
+        state, inc = _pcg_seeded(11 + i, 1)
+        seeded[i] = reference.ex_rng(inc, state)
+    a, sa = H.bounce_rays(first, rng_state=seeded)
+    b, sb = H.bounce_rays(first, seed_base=11)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8)) and np.array_equal(sa, sb)
+    # three draws for a shadow ray (sample2D + the light pick), and pixel_of routes a compacted wave to its pixels
+    la, lb = prim.squareList[5:6], prim.squareList[6:7]
+    tex = tex0.copy()
+    sub = np.nonzero(hit)[0].astype(np.uint32)
+    rays2, src2 = H.shadow_rays(first[sub], la, lb, pixel_of=sub, rng_state=tex)
+    assert np.array_equal(src2, sub)                                   # srcIndex carries the pixel on
+    i = int(sub[3])
+    inc, state = reference.to_rng(tex0[i])
+    for _ in range(3):
+        state = _pcg_step(state, inc)
+    assert np.array_equal(tex[i], reference.ex_rng(inc, state))
+    assert np.array_equal(tex[~hit], tex0[~hit])

@@ -50,6 +50,27 @@ struct Pcg32 {
         return (xorshifted >> rot) | (xorshifted << ((-rot) & 31));
     }
     float randomF() { return ldexpf((float)next(), -32); }            // Random.metal:21-26
+    // the per-pixel state texture of the reference (RGBA32Uint): r = state >> 32, g = state, b = inc >> 32, a = inc
+    struct Raw {};
+    Pcg32(Raw, const uint32_t t[4]) {                                 // toRNG  Render.hh:96-107
+        state = ((uint64_t)t[0] << 32) | t[1];
+        inc = ((uint64_t)t[2] << 32) | t[3];
+    }
+    void store(uint32_t t[4]) const {                                 // exRNG  Render.hh:109-120
+        t[0] = (uint32_t)(state >> 32); t[1] = (uint32_t)state; t[2] = (uint32_t)(inc >> 32); t[3] = (uint32_t)inc;
+    }
+};
+
+// RNG of record i: the pixel's stored stream when a state texture is given, else PCG32(seedBase + i, 1).
+struct RngSlot {
+    Pcg32 rng;
+    uint32_t* slot;
+    uint32_t pixel;
+    RngSlot(uint64_t seedBase, uint64_t i, const uint32_t* pixelOf, uint32_t* rngState)
+        : rng(seedBase + i, 1), slot(nullptr), pixel(pixelOf ? pixelOf[i] : (uint32_t)i) {
+        if (rngState) { slot = rngState + 4 * (size_t)pixel; rng = Pcg32(Pcg32::Raw{}, slot); }
+    }
+    ~RngSlot() { if (slot) rng.store(slot); }
 };
 
 // Math.hh:57-74
@@ -221,11 +242,17 @@ void trqh_gen_camera_rays(const float lookFrom_[3], const float lookAt_[3], cons
 
 uint64_t trqh_gen_bounce_rays(const trq_hit_record* recs, uint64_t n, uint64_t seedBase,
                               trq_ray* rays, uint32_t* srcIndex) {
+    return trqh_gen_bounce_rays_rng(recs, n, seedBase, nullptr, nullptr, rays, srcIndex);
+}
+
+uint64_t trqh_gen_bounce_rays_rng(const trq_hit_record* recs, uint64_t n, uint64_t seedBase, const uint32_t* pixelOf,
+                                  uint32_t* rngState, trq_ray* rays, uint32_t* srcIndex) {
     uint64_t k = 0;
     for (uint64_t i = 0; i < n; ++i) {
         const trq_hit_record& h = recs[i];
         if (!h.hit) continue;
-        Pcg32 rng(seedBase + i, 1);
+        RngSlot rs(seedBase, i, pixelOf, rngState);
+        Pcg32& rng = rs.rng;
         float u0 = rng.randomF(), u1 = rng.randomF();                                 // xsampler.sample2D()  Render.metal:447
         V3 p{h.p[0], h.p[1], h.p[2]}, sn{h.sn[0], h.sn[1], h.sn[2]};
         V3 origin = offset_ray(p, sn);                                                // :450
@@ -235,7 +262,7 @@ uint64_t trqh_gen_bounce_rays(const trq_hit_record* recs, uint64_t n, uint64_t s
         V3 dir = nx * wi.x + ny * wi.y + sn * wi.z;                                   // stw * wi  :475
         dir = normalize(dir);                                                         // ray.update -> normalize  Ray.hh:25-28
         store_ray(rays[k], origin, dir, FLT_MAX);
-        if (srcIndex) srcIndex[k] = (uint32_t)i;
+        if (srcIndex) srcIndex[k] = rs.pixel;
         ++k;
     }
     return k;
@@ -243,12 +270,18 @@ uint64_t trqh_gen_bounce_rays(const trq_hit_record* recs, uint64_t n, uint64_t s
 
 uint64_t trqh_gen_shadow_rays(const trq_hit_record* recs, uint64_t n, uint64_t seedBase,
                               const void* lightA, const void* lightB, trq_ray* rays, uint32_t* srcIndex) {
+    return trqh_gen_shadow_rays_rng(recs, n, seedBase, nullptr, nullptr, lightA, lightB, rays, srcIndex);
+}
+
+uint64_t trqh_gen_shadow_rays_rng(const trq_hit_record* recs, uint64_t n, uint64_t seedBase, const uint32_t* pixelOf,
+                                  uint32_t* rngState, const void* lightA, const void* lightB, trq_ray* rays, uint32_t* srcIndex) {
     const trq::RefSquare* L[2] = {(const trq::RefSquare*)lightA, (const trq::RefSquare*)lightB};
     uint64_t k = 0;
     for (uint64_t i = 0; i < n; ++i) {
         const trq_hit_record& h = recs[i];
         if (!h.hit) continue;
-        Pcg32 rng(seedBase + i, 1);
+        RngSlot rs(seedBase, i, pixelOf, rngState);
+        Pcg32& rng = rs.rng;
         float u0 = rng.randomF(), u1 = rng.randomF();                                 // Render.metal:313
         V3 p{h.p[0], h.p[1], h.p[2]}, sn{h.sn[0], h.sn[1], h.sn[2]};
         V3 origin = offset_ray(p, sn);                                                // :316
@@ -268,7 +301,7 @@ uint64_t trqh_gen_shadow_rays(const trq_hit_record* recs, uint64_t n, uint64_t s
         float dis = length(dirv);                                                     // :334
         V3 d = normalize(nor);                                                        // Ray(_origin, _nor) normalises again  :335
         store_ray(rays[k], origin, d, dis);
-        if (srcIndex) srcIndex[k] = (uint32_t)i;
+        if (srcIndex) srcIndex[k] = rs.pixel;
         ++k;
     }
     return k;

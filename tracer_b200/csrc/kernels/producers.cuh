@@ -36,7 +36,23 @@ struct Pcg32Dev {
         return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
     }
     __device__ __forceinline__ float randomF() { return fmul(__uint2float_rn(next()), 2.3283064365386963e-10f); }   // ldexp(float(i), -32)
+    // the reference's per-pixel state texture (RGBA32Uint): toRNG / exRNG, Render.hh:96-120
+    __device__ __forceinline__ void load(const uint4 t) { state = ((uint64_t)t.x << 32) | t.y; inc = ((uint64_t)t.z << 32) | t.w; }
+    __device__ __forceinline__ uint4 store() const { return make_uint4((uint32_t)(state >> 32), (uint32_t)state, (uint32_t)(inc >> 32), (uint32_t)inc); }
 };
+
+// Where the draws of record i come from: the pixel's stream in the state texture (loaded here, stored back by
+// rng_release) or, without a texture, PCG32(seedBase + i, 1).
+__device__ __forceinline__ Pcg32Dev rng_acquire(uint64_t seedBase, uint64_t i, const uint32_t* __restrict__ pixelOf,
+                                                const uint32_t* rngState, uint32_t& pixel) {
+    pixel = pixelOf ? __ldg(pixelOf + i) : (uint32_t)i;
+    Pcg32Dev rng(seedBase + i, 1);
+    if (rngState) rng.load(*reinterpret_cast<const uint4*>(rngState + 4 * (size_t)pixel));
+    return rng;
+}
+__device__ __forceinline__ void rng_release(const Pcg32Dev& rng, uint32_t* rngState, uint32_t pixel) {
+    if (rngState) *reinterpret_cast<uint4*>(rngState + 4 * (size_t)pixel) = rng.store();
+}
 
 // Math.hh:57-74
 __device__ __forceinline__ f3 offset_ray_dev(const f3& p, const f3& n) {
@@ -132,15 +148,17 @@ cast_rays_kernel(CameraDev cam, uint32_t W, uint32_t H, trq_ray* __restrict__ ra
 
 __global__ void __launch_bounds__(256)
 spawn_bounce_kernel(SceneDev S, const trq_ray* __restrict__ rays, const trq_hit* __restrict__ hits, uint64_t n,
-                    const unsigned long long* __restrict__ nPtr, uint64_t seedBase,
-                    trq_ray* __restrict__ out, uint32_t* __restrict__ srcIndex, unsigned long long* counter) {
+                    const unsigned long long* __restrict__ nPtr, uint64_t seedBase, const uint32_t* __restrict__ pixelOf,
+                    uint32_t* rngState, trq_ray* __restrict__ out, uint32_t* __restrict__ srcIndex, unsigned long long* counter) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Surface s;
     const bool alive = i < live_count(n, nPtr) && surface_of_hit(S, rays, hits, i, s);
     f3 origin = make_f3(0.f, 0.f, 0.f), dir = make_f3(0.f, 0.f, 1.f);
+    uint32_t pixel = 0;
     if (alive) {
-        Pcg32Dev rng(seedBase + i, 1);
+        Pcg32Dev rng = rng_acquire(seedBase, i, pixelOf, rngState, pixel);
         const float u0 = rng.randomF(), u1 = rng.randomF();                             // xsampler.sample2D()  Render.metal:447
+        rng_release(rng, rngState, pixel);
         origin = offset_ray_dev(s.p, s.sn);                                             // :450
         f3 nx, ny;
         coordinate_system_dev(s.sn, nx, ny);                                            // :453-455
@@ -151,25 +169,27 @@ spawn_bounce_kernel(SceneDev S, const trq_ray* __restrict__ rays, const trq_hit*
     const uint64_t k = warp_push(alive, counter);
     if (alive) {
         write_ray(out, k, origin, dir, FLT_MAX);
-        if (srcIndex) srcIndex[k] = (uint32_t)i;
+        if (srcIndex) srcIndex[k] = pixel;
     }
 }
 
 __global__ void __launch_bounds__(256)
 spawn_shadow_kernel(SceneDev S, const trq_ray* __restrict__ rays, const trq_hit* __restrict__ hits, uint64_t n,
-                    const unsigned long long* __restrict__ nPtr, uint64_t seedBase,
-                    uint32_t lightA, uint32_t lightB, trq_ray* __restrict__ out, uint32_t* __restrict__ srcIndex,
-                    unsigned long long* counter) {
+                    const unsigned long long* __restrict__ nPtr, uint64_t seedBase, const uint32_t* __restrict__ pixelOf,
+                    uint32_t* rngState, uint32_t lightA, uint32_t lightB, trq_ray* __restrict__ out,
+                    uint32_t* __restrict__ srcIndex, unsigned long long* counter) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     Surface s;
     const bool alive = i < live_count(n, nPtr) && surface_of_hit(S, rays, hits, i, s);
     f3 origin = make_f3(0.f, 0.f, 0.f), dir = make_f3(0.f, 0.f, 1.f);
     float dis = 0.0f;
+    uint32_t pixel = 0;
     if (alive) {
-        Pcg32Dev rng(seedBase + i, 1);
+        Pcg32Dev rng = rng_acquire(seedBase, i, pixelOf, rngState, pixel);
         const float u0 = rng.randomF(), u1 = rng.randomF();                             // Render.metal:313
         origin = offset_ray_dev(s.p, s.sn);                                             // :316
         const RefSquare* sq = &S.squares[(rng.randomF() < 0.5f) ? lightA : lightB];     // :319-323
+        rng_release(rng, rngState, pixel);
         // Square::sample  Square.hh:40-58
         f3 lp = make_f3(0.f, 0.f, 0.f);
         set3(lp, sq->axis_k, sq->value_k);
@@ -188,7 +208,7 @@ spawn_shadow_kernel(SceneDev S, const trq_ray* __restrict__ rays, const trq_hit*
     const uint64_t k = warp_push(alive, counter);
     if (alive) {
         write_ray(out, k, origin, dir, dis);
-        if (srcIndex) srcIndex[k] = (uint32_t)i;
+        if (srcIndex) srcIndex[k] = pixel;
     }
 }
 

@@ -638,7 +638,13 @@ static int spawn_common(trq_scene* s, const trq_ray* rays, const trq_hit* hits, 
 
 int trq_spawn_bounce(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n, uint64_t seedBase,
                      trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream) {
+    return trq_spawn_bounce_rng(s, rays, hits, n, d_n, seedBase, nullptr, nullptr, out, srcIndex, d_count, stream);
+}
+
+int trq_spawn_bounce_rng(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n, uint64_t seedBase,
+                         const uint32_t* pixelOf, uint32_t* rngState, trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream) {
     int rc = spawn_common(s, rays, hits, n, d_n, d_count, "trq_spawn_bounce");
+    if (rc == TRQ_OK && rngState && (((uintptr_t)rngState) & 15u)) rc = trq::fail(TRQ_ERR_INVALID, "trq_spawn_bounce_rng: rngState must be 16-byte aligned");
     if (rc != TRQ_OK) return rc;
     if (n && !out) return trq::fail(TRQ_ERR_INVALID, "trq_spawn_bounce: NULL out");
     DeviceGuard guard(s->device);
@@ -646,7 +652,7 @@ int trq_spawn_bounce(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uin
     cudaStream_t st = (cudaStream_t)stream;
     TRQ_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     if (n == 0) return TRQ_OK;
-    spawn_bounce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, rays, hits, n, (const unsigned long long*)d_n, seedBase, out, srcIndex,
+    spawn_bounce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, rays, hits, n, (const unsigned long long*)d_n, seedBase, pixelOf, rngState, out, srcIndex,
                                                                       (unsigned long long*)d_count);
 
     g_launches++;
@@ -656,7 +662,14 @@ int trq_spawn_bounce(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uin
 
 int trq_spawn_shadow(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n, uint64_t seedBase,
                      uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream) {
+    return trq_spawn_shadow_rng(s, rays, hits, n, d_n, seedBase, nullptr, nullptr, lightA, lightB, out, srcIndex, d_count, stream);
+}
+
+int trq_spawn_shadow_rng(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n, uint64_t seedBase,
+                         const uint32_t* pixelOf, uint32_t* rngState, uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex,
+                         uint64_t* d_count, void* stream) {
     int rc = spawn_common(s, rays, hits, n, d_n, d_count, "trq_spawn_shadow");
+    if (rc == TRQ_OK && rngState && (((uintptr_t)rngState) & 15u)) rc = trq::fail(TRQ_ERR_INVALID, "trq_spawn_shadow_rng: rngState must be 16-byte aligned");
     if (rc != TRQ_OK) return rc;
     if (n && !out) return trq::fail(TRQ_ERR_INVALID, "trq_spawn_shadow: NULL out");
     if (lightA >= s->info.nSquare || lightB >= s->info.nSquare)
@@ -666,7 +679,7 @@ int trq_spawn_shadow(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uin
     cudaStream_t st = (cudaStream_t)stream;
     TRQ_CUDA(cudaMemsetAsync(d_count, 0, sizeof(uint64_t), st));
     if (n == 0) return TRQ_OK;
-    spawn_shadow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, rays, hits, n, (const unsigned long long*)d_n, seedBase, lightA, lightB, out, srcIndex,
+    spawn_shadow_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, rays, hits, n, (const unsigned long long*)d_n, seedBase, pixelOf, rngState, lightA, lightB, out, srcIndex,
                                                                       (unsigned long long*)d_count);
     g_launches++;
     TRQ_CUDA(cudaGetLastError());

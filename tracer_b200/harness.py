@@ -364,21 +364,33 @@ def random_rays(n, seed=2, lo=(0, 0, 0), hi=(1, 1, 1), tmax=L.FLT_MAX, first=0):
     return rays
 
 
-def bounce_rays(records, seed_base=0):
-    """Diffuse bounce rays spawned from hit records (Render.metal:447-475); compacted."""
+def _opt(a, dtype):
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data
+
+
+def bounce_rays(records, seed_base=0, pixel_of=None, rng_state=None):
+    """Diffuse bounce rays spawned from hit records (Render.metal:447-475); compacted. rng_state: (pixels, 4) uint32
+    array in the reference's RNG texture format (Render.hh:96-120), advanced IN PLACE when it is a contiguous uint32 array."""
     records = np.ascontiguousarray(records)
     rays = np.empty(records.size, dtype=L.ray_dtype)
     src = np.empty(records.size, dtype=np.uint32)
-    k = lib.trqh_gen_bounce_rays(records.ctypes.data, records.size, seed_base, rays.ctypes.data, src.ctypes.data)
+    _, pp = _opt(pixel_of, np.uint32)
+    _, rp = _opt(rng_state, np.uint32)
+    k = lib.trqh_gen_bounce_rays_rng(records.ctypes.data, records.size, seed_base, pp, rp, rays.ctypes.data, src.ctypes.data)
     return rays[:k].copy(), src[:k].copy()
 
 
-def shadow_rays(records, light_a, light_b, seed_base=0):
+def shadow_rays(records, light_a, light_b, seed_base=0, pixel_of=None, rng_state=None):
     """NEE shadow rays toward two light squares (Render.metal:313-337); compacted."""
     records = np.ascontiguousarray(records)
     la = np.ascontiguousarray(light_a); lb = np.ascontiguousarray(light_b)
     rays = np.empty(records.size, dtype=L.ray_dtype)
     src = np.empty(records.size, dtype=np.uint32)
-    k = lib.trqh_gen_shadow_rays(records.ctypes.data, records.size, seed_base, la.ctypes.data, lb.ctypes.data,
-                                 rays.ctypes.data, src.ctypes.data)
+    _, pp = _opt(pixel_of, np.uint32)
+    _, rp = _opt(rng_state, np.uint32)
+    k = lib.trqh_gen_shadow_rays_rng(records.ctypes.data, records.size, seed_base, pp, rp, la.ctypes.data, lb.ctypes.data,
+                                     rays.ctypes.data, src.ctypes.data)
     return rays[:k].copy(), src[:k].copy()

@@ -179,25 +179,31 @@ class Scene:
                                      self._stream(stream)), "trq_trace_indirect")
         return hits
 
-    def _spawn(self, fn, rays, hits, count_in, seed_base, extra, out, src, count, stream):
+    def _spawn(self, fn, rays, hits, count_in, seed_base, pixel_of, rng_state, extra, out, src, count, stream):
         import torch
         n = rays.shape[0]
         dev = rays.device
         out = out if out is not None else torch.empty((n, 8), dtype=torch.float32, device=dev)
         src = src if src is not None else torch.empty(n, dtype=torch.int32, device=dev)
         count = count if count is not None else torch.zeros(1, dtype=torch.int64, device=dev)
-        args = [self._h, rays.data_ptr(), hits.data_ptr(), n, None if count_in is None else count_in.data_ptr(), int(seed_base)]
+        args = [self._h, rays.data_ptr(), hits.data_ptr(), n, None if count_in is None else count_in.data_ptr(), int(seed_base),
+                None if pixel_of is None else pixel_of.data_ptr(), None if rng_state is None else rng_state.data_ptr()]
         args += list(extra) + [out.data_ptr(), src.data_ptr(), count.data_ptr(), self._stream(stream)]
         check(fn(*args), fn.__name__)
         return out, src, count
 
-    def spawn_bounce(self, rays, hits, seed_base=0, count_in=None, out=None, src=None, count=None, stream=None):
-        """Diffuse bounce rays of the hits (Render.metal:447-475), compacted. -> (rays_out, srcIndex, count tensor)."""
-        return self._spawn(lib.trq_spawn_bounce, rays, hits, count_in, seed_base, (), out, src, count, stream)
+    def spawn_bounce(self, rays, hits, seed_base=0, count_in=None, out=None, src=None, count=None, stream=None,
+                     pixel_of=None, rng_state=None):
+        """Diffuse bounce rays of the hits (Render.metal:447-475), compacted. -> (rays_out, srcIndex, count tensor).
+        rng_state: (pixels, 4) int32 CUDA tensor in the reference's RNG texture format (Render.hh:96-120), advanced in
+        place; pixel_of: int32 tensor mapping input ray -> pixel (then srcIndex holds pixels too)."""
+        return self._spawn(lib.trq_spawn_bounce_rng, rays, hits, count_in, seed_base, pixel_of, rng_state, (), out, src, count, stream)
 
-    def spawn_shadow(self, rays, hits, light_a, light_b, seed_base=0, count_in=None, out=None, src=None, count=None, stream=None):
+    def spawn_shadow(self, rays, hits, light_a, light_b, seed_base=0, count_in=None, out=None, src=None, count=None, stream=None,
+                     pixel_of=None, rng_state=None):
         """NEE shadow rays toward squareList[light_a|light_b] (Render.metal:313-337), compacted."""
-        return self._spawn(lib.trq_spawn_shadow, rays, hits, count_in, seed_base, (int(light_a), int(light_b)), out, src, count, stream)
+        return self._spawn(lib.trq_spawn_shadow_rng, rays, hits, count_in, seed_base, pixel_of, rng_state,
+                           (int(light_a), int(light_b)), out, src, count, stream)
 
     def profile(self, on=True):
         check(lib.trq_profile_enable(self._h, 1 if on else 0), "trq_profile_enable")
