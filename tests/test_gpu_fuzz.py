@@ -2,6 +2,8 @@
 direction components (1/0 = inf slabs), origins lying exactly on box planes / vertices / edges (0 * inf = NaN inside
 AABB::hit_t, where only fminf/fmaxf's NaN rule decides), degenerate and duplicated triangles, tiny and huge tmax,
 mixed leaf types, any-hit and closest-hit, both kernels."""
+import os
+
 import numpy as np
 import pytest
 
@@ -72,7 +74,16 @@ def scenes(rng):
     yield "spheres", H.build_primitive(spheres=sph)
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
+def _seeds():
+    """Three seeds in the regular suite; TRQ_FUZZ_SEEDS=lo-hi widens the campaign (profiles/r01_fuzz_campaign.txt)."""
+    extra = os.environ.get("TRQ_FUZZ_SEEDS", "")
+    if "-" in extra:
+        lo, hi = (int(x) for x in extra.split("-"))
+        return [1, 2, 3] + list(range(lo, hi + 1))
+    return [1, 2, 3]
+
+
+@pytest.mark.parametrize("seed", _seeds())
 def test_adversarial_parity(built, port, seed):
     _torch()
     from tracer_b200 import Scene
