@@ -25,6 +25,17 @@ r1, s1, c1 = scene.spawn_bounce(r0, h0, seed_base=3)
 h1 = scene.hit_indirect(r1, c1)
 sh, s2, c2 = scene.spawn_shadow(r1, h1, 5, 6, seed_base=5, count_in=c1)
 scene.hit_indirect(sh, c2, any=True)
+# the RNG-texture producers (row f-4) and the single-rank gather path (resolve_hits_kernel<GATHER>, gather_wait_kernel)
+tex = torch.randint(-2**31, 2**31 - 1, (r0.shape[0], 4), dtype=torch.int32, device=r0.device)
+r2, s3, c3 = scene.spawn_bounce(r0, h0, rng_state=tex)
+scene.spawn_shadow(r2, scene.hit_indirect(r2, c3), 5, 6, count_in=c3, pixel_of=s3, rng_state=tex)
+from tracer_b200 import dist as D  # noqa: E402
+hg = D.HitGather(scene, r0.shape[0])
+for _ in range(3):
+    hg.trace(r0); hits_all, counts = hg.wait()
+torch.cuda.synchronize(); hg.status()
+assert int(counts[0].item()) == r0.shape[0] and torch.equal(hits_all[0].view(torch.int32), h0.view(torch.int32))
+hg.close()
 host = scene.hit(H.random_rays(5000, seed=1, lo=(-245, 0, 0), hi=(800, 555, 555)))
 b = BVHBuilder(); b.buildNodesTriangles(prim.triList, prim.idxList)
 g = b.buildTree(gpu=0)
