@@ -363,7 +363,13 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 const bool onInterior = active && TRQ_REF_KIND(cur) == REF_INTERIOR;
                 const int nInt = __popc(__ballot_sync(0xffffffffu, onInterior));
                 const int nWait = __popc(__ballot_sync(0xffffffffu, active && !onInterior));
-                if (nInt == 0 || nWait >= (int)P.leafBatch || nWait > nInt) break;
+                // leave the interior phase once the lanes waiting at a leaf are more than half of those still stepping
+                // (B200 sweep, C3 / 1 M soup Mrays/s: never 4094 / 1141, nWait > nInt 4650 / 1154, 2 nWait > nInt 4727 / 1158,
+                // 3x 4701 / 1157, 4x 4678 / 1158, 6x 4614 / 1155)
+#ifndef TRQ_WAIT_MUL
+#define TRQ_WAIT_MUL 2
+#endif
+                if (nInt == 0 || nWait >= (int)P.leafBatch || TRQ_WAIT_MUL * nWait > nInt) break;
 #pragma unroll
                 for (int rep = 0; rep < TRQ_INTERIOR_UNROLL; ++rep) {          // steps per vote round
 #ifdef TRQ_STATS
