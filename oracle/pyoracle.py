@@ -226,6 +226,48 @@ class Reference:
         return out
 
 
+REF_BUILDER_PATH = os.path.join(_HERE, "_ref", "libtracer_ref_builder.so")
+
+
+class ReferenceBuilder:
+    """The reference's own host BVH builder (BVH.hh:30-314) compiled from its source (oracle/ref_builder.cpp)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_BUILDER_PATH)
+
+    def __init__(self):
+        if not os.path.exists(REF_BUILDER_PATH):
+            if os.path.isdir("/root/reference/RT_Metal/Metal"):
+                build(("ref",))
+            else:
+                raise FileNotFoundError(REF_BUILDER_PATH)
+        self.lib = C.CDLL(REF_BUILDER_PATH)
+        self.lib.refb_build_tree.restype = C.c_uint32
+
+    def build_tree(self, leaves):
+        """BVH::buildTree over a copy of `leaves` (numpy bvh_dtype); returns the 2n-1 nodes. The two padding words of a node
+        are uninitialised in the reference (struct BVH has none of its own): zeroed here."""
+        leaves = np.ascontiguousarray(leaves)
+        n = leaves.size
+        nodes = np.zeros(max(2 * n - 1, 1), dtype=leaves.dtype)
+        nodes[:n] = leaves
+        k = self.lib.refb_build_tree(C.c_void_p(nodes.ctypes.data), C.c_uint32(n))
+        assert k == nodes.size, (k, nodes.size)
+        nodes["pad"] = 0
+        return nodes
+
+    def build_node(self, box_min, box_max, model, p_type, p_index, dtype):
+        lo, hi = _fp(box_min), _fp(box_max)
+        m = None if model is None else np.ascontiguousarray(model, dtype=np.float32).reshape(16)
+        out = np.zeros(1, dtype=dtype)
+        self.lib.refb_build_node(C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data),
+                                 C.c_void_p(m.ctypes.data if m is not None else None), C.c_int32(p_type), C.c_uint32(p_index),
+                                 C.c_void_p(out.ctypes.data))
+        out["pad"] = 0
+        return out[0]
+
+
 NEXTWEEK_PATH = os.path.join(_HERE, "libnextweek_bvh.so")
 
 

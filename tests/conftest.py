@@ -27,6 +27,14 @@ def port(built):
 
 
 @pytest.fixture(scope="session")
+def reference_builder(built):
+    from oracle.pyoracle import ReferenceBuilder
+    if not ReferenceBuilder.available():
+        pytest.skip("oracle/_ref builder not built (no /root/reference on this box)")
+    return ReferenceBuilder()
+
+
+@pytest.fixture(scope="session")
 def reference(built):
     from oracle.pyoracle import Reference
     if not Reference.available():

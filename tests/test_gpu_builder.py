@@ -109,3 +109,20 @@ def test_gpu_build_identical_centroids_is_still_a_valid_tree(built, port):
     for k in ("flags", "pType", "pIndex", "leafNode"):
         assert np.array_equal(got[k], want[k])
     assert np.array_equal(got["t"], ref["t"]) and np.array_equal(got["flags"] & 1, ref["flags"] & 1)
+
+
+@pytest.mark.parametrize("name", ["soup2", "soup3", "soup7", "soup100", "soup2000", "cornell_mixed"])
+def test_gpu_tree_equals_reference_builder_golden(built, name):
+    """The GPU builder against trees made by the REFERENCE's own BVH::buildTree (tests/golden/bvh_golden.npz, generated by
+    tests/golden/make_bvh_golden.py from oracle/_ref/libtracer_ref_builder.so)."""
+    import os
+    _torch()
+    from tracer_b200._lib import check, lib
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bvh_golden.npz"))
+    leaves, want = z[f"{name}/leaves"], z[f"{name}/tree"]
+    n = leaves.size
+    nodes = np.zeros(2 * n - 1, dtype=L.bvh_dtype)
+    nodes[:n] = leaves
+    nn, d = C.c_uint32(0), C.c_uint32(0)
+    check(lib.trq_bvh_build_tree_gpu(nodes.ctypes.data, n, 0, C.byref(nn), C.byref(d)), "gpu build")
+    assert_same_tree(nodes, want)

@@ -13,9 +13,10 @@
 // node's final index is known before its subtree is built, so the top levels are built on
 // worker threads here WITHOUT changing the numbering.
 //
-// The reference builder cannot be compiled in this environment (clang blocks, libdispatch,
-// Apple simd), so there is no executable oracle for it: tests pin it through structural
-// invariants and through brute-force ray queries ("builder parity").
+// Parity: the reference builder itself is compiled from its source as test infrastructure
+// (oracle/ref_builder.cpp: blocks -> lambdas on the way into g++, libdispatch and Apple simd as
+// small stand-ins, dispatch_async run in place = this sequential order); this file reproduces its
+// node arrays byte for byte (tests/test_builder.py, tests/golden/bvh_golden.npz).
 
 #include "../../../include/tracer_rq.h"
 #include "error.h"
