@@ -268,6 +268,54 @@ class ReferenceBuilder:
         return out[0]
 
 
+REF_SETUP_PATH = os.path.join(_HERE, "_ref", "libtracer_ref_setup.so")
+
+
+class ReferenceSetup:
+    """The reference's scene set-up code (RT_Metal/Tracer/Tracer.mm) compiled from its source (oracle/ref_scene_setup.cpp)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SETUP_PATH)
+
+    def __init__(self):
+        if not os.path.exists(REF_SETUP_PATH):
+            if os.path.isdir("/root/reference/RT_Metal/Tracer"):
+                build(("ref",))
+            else:
+                raise FileNotFoundError(REF_SETUP_PATH)
+        self.lib = C.CDLL(REF_SETUP_PATH)
+        for fn in (self.lib.refs_cornell_squares, self.lib.refs_cubes, self.lib.refs_spheres, self.lib.refs_material_count):
+            fn.restype = C.c_uint32
+
+    def _fetch(self, fn, dtype):
+        n = fn(None, 0)
+        a = np.zeros(n, dtype=dtype)
+        fn(C.c_void_p(a.ctypes.data), n)
+        return a
+
+    def squares(self):
+        return self._fetch(self.lib.refs_cornell_squares, L.square_dtype)
+
+    def cubes(self):
+        return self._fetch(self.lib.refs_cubes, L.cube_dtype)
+
+    def spheres(self):
+        return self._fetch(self.lib.refs_spheres, L.sphere_dtype)
+
+    def prepare_camera(self, view_w, view_h):
+        out = np.zeros(18, dtype=np.float32)
+        self.lib.refs_prepare_camera(C.c_float(view_w), C.c_float(view_h), C.c_void_p(out.ctypes.data))
+        return out
+
+    def make_camera(self, look_from, look_at, view_up, aperture, aspect, vfov, focus):
+        a, b, c = _fp(look_from), _fp(look_at), _fp(view_up)
+        out = np.zeros(18, dtype=np.float32)
+        self.lib.refs_make_camera(C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), C.c_void_p(c.ctypes.data), C.c_float(aperture),
+                                  C.c_float(aspect), C.c_float(vfov), C.c_float(focus), C.c_void_p(out.ctypes.data))
+        return out
+
+
 NEXTWEEK_PATH = os.path.join(_HERE, "libnextweek_bvh.so")
 
 

@@ -28,4 +28,4 @@ inline long dispatch_semaphore_wait(dispatch_semaphore_t, unsigned long long) { 
 inline long dispatch_semaphore_signal(dispatch_semaphore_t) { return 0; }
 template <typename F> inline void dispatch_async(dispatch_queue_t, F&& f) { f(); }
 template <typename F> inline void dispatch_sync(dispatch_queue_t, F&& f) { f(); }
-template <typename F> inline void dispatch_apply(size_t n, dispatch_queue_t, F&& f) { for (size_t i = 0; i < n; ++i) f(i); }
+template <typename F> inline void dispatch_apply(unsigned long n, dispatch_queue_t, F&& f) { for (unsigned long i = 0; i < n; ++i) f(i); }

@@ -73,3 +73,79 @@ inline simd_float4 simd_mul(const simd_float4x4& m, const simd_float4& v) {
     r = r + m.columns[3] * v.w;
     return r;
 }
+
+/* ---- what RT_Metal/Tracer/Tracer.mm uses on top of the above (scene constants, camera) -------------------------
+ * Apple's definitions, unfused fp32: dot = (x*x' + y*y') + z*z'; normalize(v) = v * (1 / sqrt(dot(v, v))) (simd/geometry.h,
+ * precise variant); matrix product column by column; 4x4 inverse by cofactors in double (Apple's is closed source: the
+ * inverse / normal matrices are compared to a tolerance, everything else exactly). */
+inline float simd_dot(const simd_float3& a, const simd_float3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline simd_float3 simd_cross(const simd_float3& a, const simd_float3& b) {
+    return simd_float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+inline float simd_length_squared(const simd_float3& a) { return simd_dot(a, a); }
+inline float simd_length(const simd_float3& a) { return sqrtf(simd_dot(a, a)); }
+inline simd_float3 simd_normalize(const simd_float3& a) { return a * (1.0f / sqrtf(simd_length_squared(a))); }
+inline simd_float3 vector_normalize(const simd_float3& a) { return simd_normalize(a); }
+inline simd_float3 simd_make_float3(float s) { return simd_float3(s); }
+
+inline simd_float4x4 simd_transpose(const simd_float4x4& m) {
+    simd_float4x4 r;
+    for (int c = 0; c < 4; ++c) for (int k = 0; k < 4; ++k) r.columns[c][k] = m.columns[k][c];
+    return r;
+}
+inline simd_float4x4 simd_mul(const simd_float4x4& a, const simd_float4x4& b) {
+    simd_float4x4 r;
+    for (int c = 0; c < 4; ++c) r.columns[c] = simd_mul(a, b.columns[c]);
+    return r;
+}
+inline simd_float4x4 simd_inverse(const simd_float4x4& m) {
+    double a[16], inv[16];
+    for (int c = 0; c < 4; ++c) for (int k = 0; k < 4; ++k) a[4 * c + k] = m.columns[c][k];
+    inv[0] = a[5] * a[10] * a[15] - a[5] * a[11] * a[14] - a[9] * a[6] * a[15] + a[9] * a[7] * a[14] + a[13] * a[6] * a[11] - a[13] * a[7] * a[10];
+    inv[4] = -a[4] * a[10] * a[15] + a[4] * a[11] * a[14] + a[8] * a[6] * a[15] - a[8] * a[7] * a[14] - a[12] * a[6] * a[11] + a[12] * a[7] * a[10];
+    inv[8] = a[4] * a[9] * a[15] - a[4] * a[11] * a[13] - a[8] * a[5] * a[15] + a[8] * a[7] * a[13] + a[12] * a[5] * a[11] - a[12] * a[7] * a[9];
+    inv[12] = -a[4] * a[9] * a[14] + a[4] * a[10] * a[13] + a[8] * a[5] * a[14] - a[8] * a[6] * a[13] - a[12] * a[5] * a[10] + a[12] * a[6] * a[9];
+    inv[1] = -a[1] * a[10] * a[15] + a[1] * a[11] * a[14] + a[9] * a[2] * a[15] - a[9] * a[3] * a[14] - a[13] * a[2] * a[11] + a[13] * a[3] * a[10];
+    inv[5] = a[0] * a[10] * a[15] - a[0] * a[11] * a[14] - a[8] * a[2] * a[15] + a[8] * a[3] * a[14] + a[12] * a[2] * a[11] - a[12] * a[3] * a[10];
+    inv[9] = -a[0] * a[9] * a[15] + a[0] * a[11] * a[13] + a[8] * a[1] * a[15] - a[8] * a[3] * a[13] - a[12] * a[1] * a[11] + a[12] * a[3] * a[9];
+    inv[13] = a[0] * a[9] * a[14] - a[0] * a[10] * a[13] - a[8] * a[1] * a[14] + a[8] * a[2] * a[13] + a[12] * a[1] * a[10] - a[12] * a[2] * a[9];
+    inv[2] = a[1] * a[6] * a[15] - a[1] * a[7] * a[14] - a[5] * a[2] * a[15] + a[5] * a[3] * a[14] + a[13] * a[2] * a[7] - a[13] * a[3] * a[6];
+    inv[6] = -a[0] * a[6] * a[15] + a[0] * a[7] * a[14] + a[4] * a[2] * a[15] - a[4] * a[3] * a[14] - a[12] * a[2] * a[7] + a[12] * a[3] * a[6];
+    inv[10] = a[0] * a[5] * a[15] - a[0] * a[7] * a[13] - a[4] * a[1] * a[15] + a[4] * a[3] * a[13] + a[12] * a[1] * a[7] - a[12] * a[3] * a[5];
+    inv[14] = -a[0] * a[5] * a[14] + a[0] * a[6] * a[13] + a[4] * a[1] * a[14] - a[4] * a[2] * a[13] - a[12] * a[1] * a[6] + a[12] * a[2] * a[5];
+    inv[3] = -a[1] * a[6] * a[11] + a[1] * a[7] * a[10] + a[5] * a[2] * a[11] - a[5] * a[3] * a[10] - a[9] * a[2] * a[7] + a[9] * a[3] * a[6];
+    inv[7] = a[0] * a[6] * a[11] - a[0] * a[7] * a[10] - a[4] * a[2] * a[11] + a[4] * a[3] * a[10] + a[8] * a[2] * a[7] - a[8] * a[3] * a[6];
+    inv[11] = -a[0] * a[5] * a[11] + a[0] * a[7] * a[9] + a[4] * a[1] * a[11] - a[4] * a[3] * a[9] - a[8] * a[1] * a[7] + a[8] * a[3] * a[5];
+    inv[15] = a[0] * a[5] * a[10] - a[0] * a[6] * a[9] - a[4] * a[1] * a[10] + a[4] * a[2] * a[9] + a[8] * a[1] * a[6] - a[8] * a[2] * a[5];
+    const double det = a[0] * inv[0] + a[1] * inv[4] + a[2] * inv[8] + a[3] * inv[12];
+    simd_float4x4 r;
+    for (int c = 0; c < 4; ++c) for (int k = 0; k < 4; ++k) r.columns[c][k] = (float)(inv[4 * c + k] / det);
+    return r;
+}
+
+struct simd_quatf { simd_float4 vector; };       /* (imaginary xyz, real w) */
+inline simd_quatf simd_quaternion(float angle, simd_float3 axis) {
+    const float s = sinf(angle / 2), c = cosf(angle / 2);
+    simd_quatf q; q.vector = simd_float4(s * axis.x, s * axis.y, s * axis.z, c);
+    return q;
+}
+inline simd_quatf simd_mul(const simd_quatf& p, const simd_quatf& q) {
+    const simd_float4 &a = p.vector, &b = q.vector;
+    simd_quatf r;
+    r.vector = simd_float4(a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+                           a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z);
+    return r;
+}
+inline simd_float3 simd_act(const simd_quatf& q, const simd_float3& v) {      /* v + 2 w (u x v) + 2 u x (u x v) */
+    const simd_float3 u(q.vector.x, q.vector.y, q.vector.z);
+    const simd_float3 t = simd_cross(u, v) * 2.0f;
+    return v + t * q.vector.w + simd_cross(u, t);
+}
+
+namespace simd {
+inline simd_float3 normalize(const simd_float3& a) { return simd_normalize(a); }
+inline simd_float3 cross(const simd_float3& a, const simd_float3& b) { return simd_cross(a, b); }
+inline float length(const simd_float3& a) { return simd_length(a); }
+inline float dot(const simd_float3& a, const simd_float3& b) { return simd_dot(a, b); }
+inline simd_float4x4 inverse(const simd_float4x4& m) { return simd_inverse(m); }
+}  // namespace simd

@@ -35,6 +35,14 @@ def reference_builder(built):
 
 
 @pytest.fixture(scope="session")
+def reference_setup(built):
+    from oracle.pyoracle import ReferenceSetup
+    if not ReferenceSetup.available():
+        pytest.skip("oracle/_ref scene set-up not built (no /root/reference on this box)")
+    return ReferenceSetup()
+
+
+@pytest.fixture(scope="session")
 def reference(built):
     from oracle.pyoracle import Reference
     if not Reference.available():

@@ -126,3 +126,48 @@ def test_rng_state_texture_is_the_references_wire_format(reference):
         state = _pcg_step(state, inc)
     assert np.array_equal(tex[i], reference.ex_rng(inc, state))
     assert np.array_equal(tex[~hit], tex0[~hit])
+
+
+def test_scene_constants_are_the_references(reference_setup):
+    """The Cornell squares, the two BVH cubes, the 12 spheres and the camera the workloads restate, against the reference's
+    own set-up code (Tracer.mm prepareCornellBox / prepareCubeList / prepareSphereList / prepareCamera, compiled from its
+    source with the lists built in the application's order so that material indices agree)."""
+    def same(a, b, fields, where):
+        for f in fields:
+            x, y = a[f], b[f]
+            ok = np.array_equal(bits(x), bits(y)) if x.dtype.kind == "f" else np.array_equal(x, y)
+            assert ok, f"{where}.{f}: {x} vs {y}"
+
+    sq, ref_sq = H.cornell_squares(), reference_setup.squares()
+    assert sq.size == ref_sq.size == 7
+    # MakeSquare leaves normal / inverse matrices unset (Tracer.mm:127-153); nothing on the path reads them
+    same(sq, ref_sq, ("axis_i", "axis_j", "axis_k", "range_i", "range_j", "value_k", "model", "material", "box_mini", "box_maxi"), "square")
+    cu, ref_cu = H.cornell_cubes(), reference_setup.cubes()
+    assert ref_cu.size == 3 and cu.size == 2                          # the third (density volume) cube never enters the BVH
+    same(cu, ref_cu[:2], ("model", "box_mini", "box_maxi", "material"), "cube")
+    for f in ("inverse", "normal"):                                   # Apple's simd_inverse is closed source: tolerance
+        assert np.allclose(cu[f], ref_cu[:2][f], rtol=1e-6, atol=1e-9), f
+    sp, ref_sp = H.cornell_spheres(), reference_setup.spheres()
+    assert sp.size == ref_sp.size == 12
+    same(sp, ref_sp, ("radius", "center", "model", "material", "box_mini", "box_maxi"), "sphere")
+    # camera: prepareCamera(view 1920x1080, no rotation / offset) == MakeCamera with the constants the harness passes
+    want = reference_setup.prepare_camera(1920, 1080)
+    got = np.zeros(18, dtype=np.float32)
+    frm, at, up = (np.array(v, dtype=np.float32) for v in ((278, 278, -800), (278, 278, 278), (0, 1, 0)))
+    lib.trqh_make_camera(frm.ctypes.data, at.ctypes.data, up.ctypes.data, np.float32(45 * (np.pi / 180)),
+                         np.float32(1920) / np.float32(1080), np.float32(10.0), got.ctypes.data)
+    assert np.array_equal(bits(got), bits(want)), (got, want)
+    rng = np.random.default_rng(8)
+    for _ in range(20):                                               # MakeCamera for arbitrary cameras
+        frm, at = rng.uniform(-5, 5, 3).astype(np.float32), rng.uniform(-5, 5, 3).astype(np.float32)
+        vfov, aspect, focus = np.float32(rng.uniform(0.3, 1.5)), np.float32(rng.uniform(0.5, 2.5)), np.float32(rng.uniform(1, 20))
+        want = reference_setup.make_camera(frm, at, up, 0.0, aspect, vfov, focus)
+        lib.trqh_make_camera(frm.ctypes.data, at.ctypes.data, up.ctypes.data, vfov, aspect, focus, got.ctypes.data)
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-6)           # simd_normalize multiplies by 1/sqrt, the restatement divides
+
+
+def test_scene_constants_frozen():
+    """The same constants without the reference build (runs on the GPU box too): material numbering in application order."""
+    assert list(H.cornell_squares()["material"]) == [5, 4, 6, 6, 6, 3, 3]
+    assert list(H.cornell_cubes()["material"]) == [0, 19]
+    assert list(H.cornell_spheres()["material"]) == list(range(7, 19))

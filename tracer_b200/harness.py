@@ -66,8 +66,10 @@ def make_square(axis_i, range_i, axis_j, range_j, axis_k, k, material=0):
 
 
 def cornell_squares():
-    """prepareCornellBox (Tracer.mm:245-304): order left, right, top, back, bottom, light, little light."""
-    light, red, green, white = 0, 1, 2, 3
+    """prepareCornellBox (Tracer.mm:245-304): order left, right, top, back, bottom, light, little light.
+    Material indices as the application numbers them: one shared list filled by prepareCubeList (3 materials), then
+    prepareCornellBox (light, red, green, white), then prepareSphereList (AAPLRenderer.mm:216,222,228)."""
+    light, red, green, white = 3, 4, 5, 6
     return np.array([
         make_square(1, (0, 555), 2, (0, 555), 0, -245, green),
         make_square(1, (0, 555), 2, (0, 555), 0, 800, red),
@@ -89,10 +91,11 @@ def make_cube(model, material):
 
 
 def cornell_cubes():
-    """prepareCubeList (Tracer.mm:174-243): bigger, smaller (the density-volume third cube is not in the BVH)."""
+    """prepareCubeList (Tracer.mm:174-243): bigger (material 0: the first material the application creates), smaller
+    (the literal 19); the density-volume third cube is not in the BVH."""
     bigger = translation4x4(265, 1, 295) @ rotation4x4(math.pi * 15 / 180, (0, 1, 0)) @ scale4x4(165, 330, 165)
     smaller = translation4x4(130, 1, 65) @ rotation4x4(-0.1 * math.pi, (0, 1, 0)) @ scale4x4(165, 165, 165)
-    return np.array([make_cube(bigger, 4), make_cube(smaller, 19)], dtype=L.cube_dtype)
+    return np.array([make_cube(bigger, 0), make_cube(smaller, 19)], dtype=L.cube_dtype)
 
 
 def make_sphere(r, c, material=0):
@@ -109,9 +112,9 @@ def make_sphere(r, c, material=0):
 
 def cornell_spheres():
     """prepareSphereList (Tracer.mm:306-369)."""
-    out = [make_sphere(64, (200, 250, 200), 5)]
-    out += [make_sphere(40, (100 * (5 - i), 50, 50), 6 + i) for i in range(6)]
-    out += [make_sphere(40, (-10 + 150 * i, 500, 400), 12 + i) for i in range(5)]
+    out = [make_sphere(64, (200, 250, 200), 7)]                  # materials 7..18 (after 3 cube + 4 Cornell materials)
+    out += [make_sphere(40, (100 * (5 - i), 50, 50), 8 + i) for i in range(6)]
+    out += [make_sphere(40, (-10 + 150 * i, 500, 400), 14 + i) for i in range(5)]
     return np.array(out, dtype=L.sphere_dtype)
 
 
