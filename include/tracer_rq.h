@@ -182,12 +182,17 @@ int  trq_spawn_shadow(trq_scene* scene, const trq_ray* rays, const trq_hit* hits
                       uint64_t seedBase, uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex,
                       uint64_t* d_count, void* stream);
 
-/* The two spawns drawing from the reference's per-pixel RNG state texture (row f-4: RGBA32Uint, 4 x uint32 per pixel =
- * {state >> 32, state, inc >> 32, inc}; toRNG / exRNG, Render.hh:96-120; loaded at kernel entry and stored back at exit,
- * Render.metal:511-557). Ray i belongs to pixel pixelOf[i] (NULL: i); its PCG32 stream is loaded from
- * rngState[4 * pixel], advanced by the draws and stored back, so the next bounce / the next frame continues it.
+/* The two spawns drawing from the reference's per-pixel RNG state texture (row f-4: RGBA32Uint, 4 x uint32 per pixel).
+ * The array is kept in the layout exRNG writes at kernel exit (Render.hh:109-120, Render.metal:545-556):
+ * {state >> 32, state, inc >> 32, inc}. Ray i belongs to pixel pixelOf[i] (NULL: i); its PCG32 stream is loaded from
+ * rngState[4 * pixel], advanced by the draws and stored back in the same layout, so the next wave continues it.
  * srcIndex[k] receives the PIXEL of output ray k: pass it as pixelOf of the next wave. rngState == NULL behaves like the
- * calls above (PCG32(seedBase + i, 1)). Two rays of one batch must not share a pixel. */
+ * calls above (PCG32(seedBase + i, 1)). Two rays of one batch must not share a pixel.
+ * Frame boundary: the reference's toRNG at kernel ENTRY (Render.hh:96-107) brace-initialises pcg32_t {state, inc}
+ * (Random.hh:6-12) with (inc, state), i.e. it reads the words exRNG stored as the state as the increment and vice
+ * versa -- the halves of a texel trade places once per frame. trq_rng_frame_begin applies exactly that (in place,
+ * once per frame, before the first wave); with it the array evolves like the reference's texture frame after frame. */
+int  trq_rng_frame_begin(trq_scene* scene, uint32_t* rngState, uint64_t nPixels, void* stream);
 int  trq_spawn_bounce_rng(trq_scene* scene, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n,
                           uint64_t seedBase, const uint32_t* pixelOf, uint32_t* rngState, trq_ray* out, uint32_t* srcIndex,
                           uint64_t* d_count, void* stream);

@@ -61,10 +61,11 @@ uint64_t trqh_gen_shadow_rays(const trq_hit_record* recs, uint64_t n, uint64_t s
                               const void* lightA, const void* lightB, trq_ray* rays, uint32_t* srcIndex);
 
 /* The same two producers drawing from the reference's per-pixel RNG state texture (RGBA32Uint, 4 x uint32 per pixel:
- * state >> 32, state, inc >> 32, inc -- toRNG / exRNG, Render.hh:96-120; read at kernel entry and written back at exit,
- * Render.metal:511-557): record i belongs to pixel pixelOf[i] (NULL: i), its stream is loaded from
+ * state >> 32, state, inc >> 32, inc -- the layout exRNG writes, Render.hh:109-120; see trq_rng_frame_begin in
+ * tracer_rq.h for toRNG's entry conversion): record i belongs to pixel pixelOf[i] (NULL: i), its stream is loaded from
  * rngState[4 * pixel], advanced by the draws and stored back; srcIndex[k] receives the PIXEL, so it can be passed as
  * pixelOf of the next wave. rngState == NULL falls back to PCG32(seedBase + i, 1). */
+void     trqh_rng_frame_begin(uint32_t* rngState, uint64_t nPixels);   /* host twin of trq_rng_frame_begin */
 uint64_t trqh_gen_bounce_rays_rng(const trq_hit_record* recs, uint64_t n, uint64_t seedBase, const uint32_t* pixelOf,
                                   uint32_t* rngState, trq_ray* rays, uint32_t* srcIndex);
 uint64_t trqh_gen_shadow_rays_rng(const trq_hit_record* recs, uint64_t n, uint64_t seedBase, const uint32_t* pixelOf,

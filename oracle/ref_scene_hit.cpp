@@ -33,8 +33,8 @@
 
 #include "shim/metal_stdlib"
 
-// Blank out the shading-side headers Render.hh:5-22 would pull in (not on the hot path).
-#define Random_h
+// Blank out the shading-side headers Render.hh:5-22 would pull in (not on the hot path). Random.hh stays: it only
+// declares, and its pcg32_t {state, inc} (Random.hh:6-12) is what toRNG / exRNG (Render.hh:96-120) are written against.
 #define RandomSampler_h
 #define Camera_h
 #define Light_h
@@ -264,14 +264,19 @@ void ref_cosine_sample_hemisphere(const float* u, float* out) {
 float ref_next_float_up(float v) { return NextFloatUp(v); }
 float ref_next_float_down(float v) { return NextFloatDown(v); }
 
-// the per-pixel RNG state texture <-> pcg32_t (Render.hh:96-120); out / in = {inc, state}
+// the per-pixel RNG state texture <-> pcg32_t (Render.hh:96-120); out / in = {inc, state} BY MEMBER NAME.
+// toRNG brace-initialises `pcg32_t { rng_inc, rng_state }` positionally against a struct declared {state, inc}
+// (Random.hh:6-12), so the texel words it calls "state" (r, g) land in .inc and (b, a) in .state, while exRNG writes
+// .state to (r, g) and .inc to (b, a): the two halves of a texel trade places once per frame. That is the reference's
+// behaviour and it is what these two exports expose.
 void ref_to_rng(const uint32_t* rgba, uint64_t* inc_state) {
     vec<uint32_t, 4> c; c.r = rgba[0]; c.g = rgba[1]; c.b = rgba[2]; c.a = rgba[3];
     pcg32_t r = toRNG(c);
     inc_state[0] = r.inc; inc_state[1] = r.state;
 }
 void ref_ex_rng(const uint64_t* inc_state, uint32_t* rgba) {
-    pcg32_t r = { inc_state[0], inc_state[1] };
+    pcg32_t r;
+    r.inc = inc_state[0]; r.state = inc_state[1];
     vec<uint32_t, 4> c = exRNG(r);
     rgba[0] = c.r; rgba[1] = c.g; rgba[2] = c.b; rgba[3] = c.a;
 }

@@ -117,6 +117,9 @@ def test_rng_state_texture_two_waves(cornell):
     tex0 = rng.integers(0, 1 << 32, size=(W * Hh, 4), dtype=np.uint64).astype(np.uint32)
     tex_d = torch.from_numpy(tex0.view(np.int32)).to("cuda:0")
     tex_h = tex0.copy()
+    scene.rng_frame_begin(tex_d); H.rng_frame_begin(tex_h)             # the reference's kernel-entry conversion, once per frame
+    assert np.array_equal(tex_d.cpu().numpy().view(np.uint32), tex_h) and np.array_equal(tex_h[:, :2], tex0[:, 2:])
+    begun = tex_h.copy()
     # wave 1: bounce rays of the primary hits
     r1, s1, c1 = scene.spawn_bounce(d, hits, rng_state=tex_d)
     recs0 = scene.expand(d, hits).cpu().numpy().view(L.record_dtype).reshape(-1)
@@ -146,4 +149,4 @@ def test_rng_state_texture_two_waves(cornell):
     g2 = _np_rays(sh, n2)[order2]
     w2s = w2[np.argsort(ws2, kind="stable")]
     assert np.array_equal(bits(g2["o"]), bits(w2s["o"])) and np.array_equal(bits(g2["d"]), bits(w2s["d"]))
-    assert (tex_h != tex0).any(axis=1).sum() == n1                      # exactly the pixels that hit drew numbers
+    assert (tex_h != begun).any(axis=1).sum() == n1                      # exactly the pixels that hit drew numbers

@@ -92,7 +92,12 @@ def _pcg_seeded(seed, seq):
 
 def test_rng_state_texture_is_the_references_wire_format(reference):
     """Row f-4: the spawns draw from / write back the per-pixel RNG texture exactly as Render.metal:511-557 does
-    (toRNG / exRNG, Render.hh:96-120, executed from the verbatim build)."""
+    (toRNG / exRNG, Render.hh:96-120, executed from the verbatim build) -- including toRNG's quirk: it fills
+    pcg32_t {state, inc} positionally with (inc, state), so the halves of a texel trade places at every kernel entry."""
+    probe = np.array([0x11111111, 0x22222222, 0x33333333, 0x44444444], dtype=np.uint32)
+    inc, state = reference.to_rng(probe)
+    assert (inc, state) == (0x1111111122222222, 0x3333333344444444)       # (r, g) -> .inc, (b, a) -> .state
+    assert list(reference.ex_rng(inc, state)) == [0x33333333, 0x44444444, 0x11111111, 0x22222222]
     prim = H.scene_reference_cornell()
     first = reference.trace(prim, H.cornell_camera_rays(48, 27))
     n = first.size
@@ -100,8 +105,10 @@ def test_rng_state_texture_is_the_references_wire_format(reference):
     rng = np.random.default_rng(5)
     tex0 = rng.integers(0, 1 << 32, size=(n, 4), dtype=np.uint64).astype(np.uint32)
     tex = tex0.copy()
+    H.rng_frame_begin(tex)                                             # the reference's kernel entry
     rays, src = H.bounce_rays(first, rng_state=tex)
-    assert np.array_equal(tex[~hit], tex0[~hit])                       # a pixel that spawns nothing draws nothing
+    for i in np.nonzero(~hit)[0][::17]:                                # a pixel that spawns nothing draws nothing:
+        assert np.array_equal(tex[i], reference.ex_rng(*reference.to_rng(tex0[i])))   # entry + exit only
     for i in np.nonzero(hit)[0][::29]:
         inc, state = reference.to_rng(tex0[i])
         state = _pcg_step(_pcg_step(state, inc), inc)                  # sample2D = two draws
@@ -117,6 +124,8 @@ def test_rng_state_texture_is_the_references_wire_format(reference):
     # three draws for a shadow ray (sample2D + the light pick), and pixel_of routes a compacted wave to its pixels
     la, lb = prim.squareList[5:6], prim.squareList[6:7]
     tex = tex0.copy()
+    H.rng_frame_begin(tex)
+    begun = tex.copy()
     sub = np.nonzero(hit)[0].astype(np.uint32)
     rays2, src2 = H.shadow_rays(first[sub], la, lb, pixel_of=sub, rng_state=tex)
     assert np.array_equal(src2, sub)                                   # srcIndex carries the pixel on
@@ -125,7 +134,7 @@ def test_rng_state_texture_is_the_references_wire_format(reference):
     for _ in range(3):
         state = _pcg_step(state, inc)
     assert np.array_equal(tex[i], reference.ex_rng(inc, state))
-    assert np.array_equal(tex[~hit], tex0[~hit])
+    assert np.array_equal(tex[~hit], begun[~hit])
 
 
 def test_scene_constants_are_the_references(reference_setup):

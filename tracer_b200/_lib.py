@@ -51,13 +51,13 @@ ABI_SYMBOLS = [
     "trq_scene_create", "trq_scene_destroy", "trq_scene_info",
     "trq_trace", "trq_host_sync", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read", "trq_probe_bandwidth",
     "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree", "trq_bvh_build_tree_gpu",
-    "trq_cast_rays", "trq_trace_indirect", "trq_spawn_bounce", "trq_spawn_shadow", "trq_spawn_bounce_rng", "trq_spawn_shadow_rng",
+    "trq_cast_rays", "trq_trace_indirect", "trq_spawn_bounce", "trq_spawn_shadow", "trq_spawn_bounce_rng", "trq_spawn_shadow_rng", "trq_rng_frame_begin",
     "trq_gather_create", "trq_gather_connect", "trq_trace_gather", "trq_gather_wait", "trq_gather_status", "trq_gather_destroy",
 ]
 HARNESS_SYMBOLS = [
     "trqh_pcg32_fill_f32", "trqh_pcg32_fill_u32", "trqh_normalize_rays", "trqh_offset_ray",
     "trqh_make_soup", "trqh_gen_random_rays", "trqh_make_camera", "trqh_gen_camera_rays",
-    "trqh_gen_bounce_rays", "trqh_gen_shadow_rays", "trqh_gen_bounce_rays_rng", "trqh_gen_shadow_rays_rng",
+    "trqh_gen_bounce_rays", "trqh_gen_shadow_rays", "trqh_gen_bounce_rays_rng", "trqh_gen_shadow_rays_rng", "trqh_rng_frame_begin",
 ]
 
 _vp, _u32, _u64, _i32, _f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32, C.c_float
@@ -85,6 +85,9 @@ lib.trq_cast_rays.argtypes = [_vp, C.POINTER(Camera), _u32, _u32, _vp, _vp]
 lib.trq_trace_indirect.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp, _vp]
 lib.trq_spawn_bounce.argtypes = [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp]
 lib.trq_spawn_shadow.argtypes = [_vp, _vp, _vp, _u64, _vp, _u64, _u32, _u32, _vp, _vp, _vp, _vp]
+lib.trq_rng_frame_begin.argtypes = [_vp, _vp, _u64, _vp]
+lib.trqh_rng_frame_begin.argtypes = [_vp, _u64]
+lib.trqh_rng_frame_begin.restype = None
 lib.trq_spawn_bounce_rng.argtypes = [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _vp, _vp, _vp, _vp]
 lib.trq_spawn_shadow_rng.argtypes = [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp, _u32, _u32, _vp, _vp, _vp, _vp]
 lib.trq_bvh_build_node.argtypes = [_vp, _vp, _vp, _i32, _u32, _vp]

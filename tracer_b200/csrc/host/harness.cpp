@@ -50,9 +50,10 @@ struct Pcg32 {
         return (xorshifted >> rot) | (xorshifted << ((-rot) & 31));
     }
     float randomF() { return ldexpf((float)next(), -32); }            // Random.metal:21-26
-    // the per-pixel state texture of the reference (RGBA32Uint): r = state >> 32, g = state, b = inc >> 32, a = inc
+    // the per-pixel state texture of the reference (RGBA32Uint) in exRNG's layout: r = state >> 32, g = state,
+    // b = inc >> 32, a = inc, on load and store (toRNG's entry swap is trqh_rng_frame_begin, once per frame)
     struct Raw {};
-    Pcg32(Raw, const uint32_t t[4]) {                                 // toRNG  Render.hh:96-107
+    Pcg32(Raw, const uint32_t t[4]) {
         state = ((uint64_t)t[0] << 32) | t[1];
         inc = ((uint64_t)t[2] << 32) | t[3];
     }
@@ -238,6 +239,14 @@ void trqh_gen_camera_rays(const float lookFrom_[3], const float lookAt_[3], cons
             store_ray(rays[i], origin, d, FLT_MAX);
         }
     });
+}
+
+void trqh_rng_frame_begin(uint32_t* rngState, uint64_t nPixels) {      // toRNG's entry quirk: see include/tracer_rq.h
+    for (uint64_t i = 0; i < nPixels; ++i) {
+        uint32_t* t = rngState + 4 * i;
+        std::swap(t[0], t[2]);
+        std::swap(t[1], t[3]);
+    }
 }
 
 uint64_t trqh_gen_bounce_rays(const trq_hit_record* recs, uint64_t n, uint64_t seedBase,

@@ -36,7 +36,8 @@ struct Pcg32Dev {
         return (xorshifted >> rot) | (xorshifted << ((0u - rot) & 31u));
     }
     __device__ __forceinline__ float randomF() { return fmul(__uint2float_rn(next()), 2.3283064365386963e-10f); }   // ldexp(float(i), -32)
-    // the reference's per-pixel state texture (RGBA32Uint): toRNG / exRNG, Render.hh:96-120
+    // the reference's per-pixel state texture (RGBA32Uint) in exRNG's layout (Render.hh:109-120):
+    // {state >> 32, state, inc >> 32, inc}, on load AND store (see rng_frame_begin_kernel for toRNG's entry quirk)
     __device__ __forceinline__ void load(const uint4 t) { state = ((uint64_t)t.x << 32) | t.y; inc = ((uint64_t)t.z << 32) | t.w; }
     __device__ __forceinline__ uint4 store() const { return make_uint4((uint32_t)(state >> 32), (uint32_t)state, (uint32_t)(inc >> 32), (uint32_t)inc); }
 };
@@ -132,6 +133,18 @@ __device__ __forceinline__ uint64_t warp_push(bool alive, unsigned long long* co
     if (m != 0u && lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(counter, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, m ? (__ffs(m) - 1) : 0);
     return base + (uint64_t)__popc(m & ((1u << lane) - 1u));
+}
+
+// toRNG at kernel entry (Render.hh:96-107, Render.metal:511-521) brace-initialises pcg32_t {state, inc} (Random.hh:6-12)
+// with (inc, state): the words exRNG stored as state come back as inc and vice versa. Applying that once per frame --
+// swapping the two halves of every texel -- and then using exRNG's layout for every wave reproduces the reference's
+// texture from frame to frame.
+__global__ void __launch_bounds__(256)
+rng_frame_begin_kernel(uint4* __restrict__ rngState, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 t = rngState[i];
+    rngState[i] = make_uint4(t.z, t.w, t.x, t.y);
 }
 
 __global__ void __launch_bounds__(256)

@@ -660,6 +660,18 @@ int trq_spawn_bounce_rng(trq_scene* s, const trq_ray* rays, const trq_hit* hits,
     return TRQ_OK;
 }
 
+int trq_rng_frame_begin(trq_scene* s, uint32_t* rngState, uint64_t nPixels, void* stream) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_rng_frame_begin: NULL scene");
+    if (nPixels == 0) return TRQ_OK;
+    if (!rngState || (((uintptr_t)rngState) & 15u)) return trq::fail(TRQ_ERR_INVALID, "trq_rng_frame_begin: rngState must be a 16-byte aligned device pointer");
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    rng_frame_begin_kernel<<<(unsigned)((nPixels + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint4*)rngState, nPixels);
+    g_launches++;
+    TRQ_CUDA(cudaGetLastError());
+    return TRQ_OK;
+}
+
 int trq_spawn_shadow(trq_scene* s, const trq_ray* rays, const trq_hit* hits, uint64_t n, const uint64_t* d_n, uint64_t seedBase,
                      uint32_t lightA, uint32_t lightB, trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream) {
     return trq_spawn_shadow_rng(s, rays, hits, n, d_n, seedBase, nullptr, nullptr, lightA, lightB, out, srcIndex, d_count, stream);

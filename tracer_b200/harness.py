@@ -374,6 +374,12 @@ def _opt(a, dtype):
     return a, a.ctypes.data
 
 
+def rng_frame_begin(rng_state):
+    """Host twin of trq_rng_frame_begin (in place on a contiguous (pixels, 4) uint32 array)."""
+    assert rng_state.dtype == np.uint32 and rng_state.flags["C_CONTIGUOUS"]
+    lib.trqh_rng_frame_begin(rng_state.ctypes.data, rng_state.shape[0])
+
+
 def bounce_rays(records, seed_base=0, pixel_of=None, rng_state=None):
     """Diffuse bounce rays spawned from hit records (Render.metal:447-475); compacted. rng_state: (pixels, 4) uint32
     array in the reference's RNG texture format (Render.hh:96-120), advanced IN PLACE when it is a contiguous uint32 array."""

@@ -192,6 +192,10 @@ class Scene:
         check(fn(*args), fn.__name__)
         return out, src, count
 
+    def rng_frame_begin(self, rng_state, stream=None):
+        """Once per frame, before the first wave: the reference's toRNG entry conversion (halves of every texel swap)."""
+        check(lib.trq_rng_frame_begin(self._h, rng_state.data_ptr(), rng_state.shape[0], self._stream(stream)), "trq_rng_frame_begin")
+
     def spawn_bounce(self, rays, hits, seed_base=0, count_in=None, out=None, src=None, count=None, stream=None,
                      pixel_of=None, rng_state=None):
         """Diffuse bounce rays of the hits (Render.metal:447-475), compacted. -> (rays_out, srcIndex, count tensor).
