@@ -211,6 +211,19 @@ class Reference:
         self.lib.ref_cosine_sample_hemisphere(C.c_void_p(u.ctypes.data), C.c_void_p(out.ctypes.data))
         return out
 
+    def pcg32(self, initstate, initseq, n):
+        """pcg32_srandom_r + n x pcg32_random_r / randomF (Random.metal:3-26) -> (uint32 array, float32 array)."""
+        u = np.zeros(n, dtype=np.uint32)
+        f = np.zeros(n, dtype=np.float32)
+        self.lib.ref_pcg32_fill(C.c_uint64(initstate), C.c_uint64(initseq), C.c_uint32(n), C.c_void_p(u.ctypes.data), C.c_void_p(f.ctypes.data))
+        return u, f
+
+    def sample2d(self, initstate, initseq):
+        """RandomSampler::sample2D (RandomSampler.hh:16-21) of a freshly seeded stream."""
+        out = np.zeros(2, dtype=np.float32)
+        self.lib.ref_sample2d(C.c_uint64(initstate), C.c_uint64(initseq), C.c_void_p(out.ctypes.data))
+        return out
+
     def to_rng(self, rgba):
         """toRNG (Render.hh:96-107): 4 x uint32 texel -> (inc, state)."""
         t = np.ascontiguousarray(rgba, dtype=np.uint32)

@@ -35,7 +35,6 @@
 
 // Blank out the shading-side headers Render.hh:5-22 would pull in (not on the hot path). Random.hh stays: it only
 // declares, and its pcg32_t {state, inc} (Random.hh:6-12) is what toRNG / exRNG (Render.hh:96-120) are written against.
-#define RandomSampler_h
 #define Camera_h
 #define Light_h
 #define Spectrum_h
@@ -49,6 +48,7 @@
 #define threadgroup
 
 #include "Render.hh"   // -I/root/reference/RT_Metal/Metal   (verbatim reference source)
+#include "Random.metal" // pcg32_srandom_r / pcg32_random_r / randomF: the definitions behind Random.hh's declarations
 
 #undef constant
 #undef thread
@@ -263,6 +263,21 @@ void ref_cosine_sample_hemisphere(const float* u, float* out) {
 }
 float ref_next_float_up(float v) { return NextFloatUp(v); }
 float ref_next_float_down(float v) { return NextFloatDown(v); }
+
+// PCG32 as the reference's kernels run it (Random.metal:3-26) and RandomSampler::sample2D (RandomSampler.hh:16-21)
+void ref_pcg32_fill(uint64_t initstate, uint64_t initseq, uint32_t n, uint32_t* u32_out, float* f32_out) {
+    pcg32_t a, b;
+    pcg32_srandom_r(&a, initstate, initseq);
+    pcg32_srandom_r(&b, initstate, initseq);
+    for (uint32_t i = 0; i < n; ++i) { u32_out[i] = pcg32_random_r(&a); f32_out[i] = randomF(&b); }
+}
+void ref_sample2d(uint64_t initstate, uint64_t initseq, float* out2) {
+    pcg32_t r;
+    pcg32_srandom_r(&r, initstate, initseq);
+    RandomSampler rs { &r };
+    float2 uu = rs.sample2D();
+    out2[0] = uu.x; out2[1] = uu.y;
+}
 
 // the per-pixel RNG state texture <-> pcg32_t (Render.hh:96-120); out / in = {inc, state} BY MEMBER NAME.
 // toRNG brace-initialises `pcg32_t { rng_inc, rng_state }` positionally against a struct declared {state, inc}

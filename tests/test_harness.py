@@ -16,6 +16,20 @@ def test_pcg32_known_answer():
     assert np.array_equal(f, np.ldexp(out.astype(np.float32), -32).astype(np.float32)) and (f >= 0).all() and (f <= 1).all()
 
 
+def test_pcg32_is_the_references(reference):
+    """The harness / producer PCG32 against the reference's own Random.metal (compiled verbatim): raw draws, randomF's
+    ldexp(float(i), -32), and RandomSampler::sample2D's draw order."""
+    rng = np.random.default_rng(4)
+    for _ in range(25):
+        seed, seq = int(rng.integers(0, 1 << 62)), int(rng.integers(0, 1 << 62))
+        want_u, want_f = reference.pcg32(seed, seq, 64)
+        got_u = np.zeros(64, dtype=np.uint32)
+        lib.trqh_pcg32_fill_u32(seed, seq, 64, got_u.ctypes.data)
+        assert np.array_equal(got_u, want_u)
+        assert np.array_equal(bits(H.pcg32_floats(seed, seq, 64)), bits(want_f))
+        assert np.array_equal(bits(H.pcg32_floats(seed, seq, 2)), bits(reference.sample2d(seed, seq)))
+
+
 def test_camera_rays_are_reference_rays(reference):
     rays = H.cornell_camera_rays(32, 18)
     assert np.allclose(np.linalg.norm(rays["d"], axis=1), 1.0, atol=1e-6)
