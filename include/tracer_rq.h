@@ -200,6 +200,19 @@ int  trq_spawn_shadow_rng(trq_scene* scene, const trq_ray* rays, const trq_hit* 
                           uint64_t seedBase, const uint32_t* pixelOf, uint32_t* rngState, uint32_t lightA, uint32_t lightB,
                           trq_ray* out, uint32_t* srcIndex, uint64_t* d_count, void* stream);
 
+/* ---- multi-GPU in one process (the reference's host is a single application) -----------------------------------
+ * One scene per device, created from the same host arrays; host rays are cut into contiguous ranges
+ * [k*n/R, (k+1)*n/R) (trq_mgpu_shard) and every range is staged and traced on its own device at the same time; the
+ * hits land in the caller's array. No collective is involved. devices == NULL: devices 0..n-1;
+ * nDevices <= 0: every visible device. trq_mgpu_scene gives the k-th scene for device-pointer work on that GPU. */
+typedef struct trq_mgpu trq_mgpu;
+int  trq_mgpu_create(const trq_scene_desc* desc, const int* devices, int nDevices, trq_mgpu** out);
+int  trq_mgpu_device_count(const trq_mgpu* m);
+trq_scene* trq_mgpu_scene(trq_mgpu* m, int k);
+int  trq_mgpu_shard(const trq_mgpu* m, uint64_t n, int k, uint64_t* lo, uint64_t* hi);
+int  trq_mgpu_trace(trq_mgpu* m, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits);
+int  trq_mgpu_destroy(trq_mgpu* m);
+
 /* ---- multi-GPU: hit gather through NVLink peer memory (one process per GPU, one node) -----------------------
  * Rays shard across ranks with no collective. A consumer that wants EVERY rank's hits whole
  * (the all-gather of trq_hit[N/R] of section 8e) gets them from the resolve kernel itself: each finished record is

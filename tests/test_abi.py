@@ -113,3 +113,19 @@ def test_gather_argument_validation_needs_no_gpu(built):
     assert lib.trq_gather_wait(None, None, None, None) != 0
     assert lib.trq_gather_status(None) != 0
     assert lib.trq_gather_destroy(None) == 0
+
+
+def test_mgpu_helper_fails_loudly_without_a_gpu(built):
+    import ctypes as C
+    import torch
+    from tracer_b200 import harness as H
+    from tracer_b200._lib import ERR_INVALID, lib
+    assert lib.trq_mgpu_create(None, None, 0, None) == ERR_INVALID
+    assert lib.trq_mgpu_device_count(None) == 0 and lib.trq_mgpu_destroy(None) == 0
+    if not torch.cuda.is_available():
+        from tracer_b200._lib import ERR_NO_DEVICE
+        prim = H.scene_soup(50, seed=1, extent=0.2)
+        h = C.c_void_p()
+        d = prim.desc()
+        assert lib.trq_mgpu_create(C.byref(d), None, 0, C.byref(h)) == ERR_NO_DEVICE
+        assert b"no CPU fallback" in lib.trq_last_error_string()

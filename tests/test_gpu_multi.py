@@ -64,3 +64,24 @@ def test_peer_memory_gather_two_ranks(built, tmp_path):
     assert p.returncode == 0, out[-4000:]
     for r in range(world):
         assert f"rank {r} ok" in out
+
+
+def test_single_process_multi_gpu_helper(built):
+    """trq_mgpu_*: one process, one scene per device, contiguous host-ray shards; identical bytes to a single-device trace
+    for ragged batch sizes (including batches smaller than the device count)."""
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from tracer_b200 import MultiGpuScene, Scene, harness as H
+    prim = H.scene_soup(100_000, seed=3, extent=0.02)
+    one = Scene(prim, 0)
+    m = MultiGpuScene(prim)
+    assert m.n_devices == torch.cuda.device_count()
+    assert [m.shard(10, k) for k in range(2)][0][0] == 0 and m.shard(10, m.n_devices - 1)[1] == 10
+    for n, any_hit in ((1_000_003, False), (257, True), (1, False), (m.n_devices - 1, False)):
+        rays = H.random_rays(n, seed=40 + n % 7)
+        want = one.hit(rays, any=any_hit)
+        got = m.hit(rays, any=any_hit)
+        assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), n
+    m.close(); one.close()

@@ -52,6 +52,7 @@ ABI_SYMBOLS = [
     "trq_trace", "trq_host_sync", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read", "trq_probe_bandwidth",
     "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree", "trq_bvh_build_tree_gpu",
     "trq_cast_rays", "trq_trace_indirect", "trq_spawn_bounce", "trq_spawn_shadow", "trq_spawn_bounce_rng", "trq_spawn_shadow_rng", "trq_rng_frame_begin",
+    "trq_mgpu_create", "trq_mgpu_device_count", "trq_mgpu_scene", "trq_mgpu_shard", "trq_mgpu_trace", "trq_mgpu_destroy",
     "trq_gather_create", "trq_gather_connect", "trq_trace_gather", "trq_gather_wait", "trq_gather_status", "trq_gather_destroy",
 ]
 HARNESS_SYMBOLS = [
@@ -75,6 +76,13 @@ lib.trq_expand_hits.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp, _vp]
 lib.trq_probe_bandwidth.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double)]
 lib.trq_profile_enable.argtypes = [_vp, C.c_int]
 lib.trq_profile_read.argtypes = [_vp, C.POINTER(_u32), C.POINTER(_f32), C.POINTER(_f32)]
+lib.trq_mgpu_create.argtypes = [C.POINTER(SceneDesc), _vp, C.c_int, C.POINTER(_vp)]
+lib.trq_mgpu_device_count.argtypes = [_vp]
+lib.trq_mgpu_scene.argtypes = [_vp, C.c_int]
+lib.trq_mgpu_scene.restype = _vp
+lib.trq_mgpu_shard.argtypes = [_vp, _u64, C.c_int, C.POINTER(_u64), C.POINTER(_u64)]
+lib.trq_mgpu_trace.argtypes = [_vp, _vp, _u64, _u32, _vp]
+lib.trq_mgpu_destroy.argtypes = [_vp]
 lib.trq_gather_create.argtypes = [_vp, _u32, _u32, _u64, C.POINTER(_vp), _vp]
 lib.trq_gather_connect.argtypes = [_vp, _vp]
 lib.trq_trace_gather.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp]

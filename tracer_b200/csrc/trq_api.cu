@@ -841,6 +841,84 @@ int trq_gather_destroy(trq_gather* g) {
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------------------
+// Single-process multi-GPU helper (SURVEY.md section 8b "multi-GPU helper trq_mgpu_* owns one scene per rank", 8e): the
+// reference's host is ONE process, so this is the form of ray sharding it can adopt without a launcher: one scene per
+// device, host rays cut into contiguous ranges [k*n/R, (k+1)*n/R), every device's range staged and traced through its
+// own copy engines and streams at once (TRQ_HOST_ASYNC on every scene, then one wait per scene). No collective anywhere:
+// the scene is replicated by uploading it R times, the hits land in the caller's host array.
+struct trq_mgpu {
+    std::vector<trq_scene*> scenes;
+};
+
+extern "C" {
+
+int trq_mgpu_create(const trq_scene_desc* desc, const int* devices, int nDevices, trq_mgpu** out) {
+    if (!desc || !out) return trq::fail(TRQ_ERR_INVALID, "trq_mgpu_create: NULL argument");
+    *out = nullptr;
+    const int have = trq_device_count();
+    if (have <= 0) return trq::fail(TRQ_ERR_NO_DEVICE, "trq_mgpu_create: no CUDA device (there is no CPU fallback)");
+    if (nDevices <= 0) nDevices = have;                        // all visible devices
+    if (nDevices > have && !devices) return trq::fail(TRQ_ERR_INVALID, "trq_mgpu_create: %d devices requested, %d visible", nDevices, have);
+    trq_mgpu* m = new (std::nothrow) trq_mgpu();
+    if (!m) return trq::fail(TRQ_ERR_NOMEM, "trq_mgpu_create: out of host memory");
+    for (int k = 0; k < nDevices; ++k) {
+        trq_scene* s = nullptr;
+        const int rc = trq_scene_create(desc, devices ? devices[k] : k, &s);
+        if (rc != TRQ_OK) {
+            for (trq_scene* t : m->scenes) trq_scene_destroy(t);
+            delete m;
+            return rc;
+        }
+        m->scenes.push_back(s);
+    }
+    *out = m;
+    return TRQ_OK;
+}
+
+int trq_mgpu_device_count(const trq_mgpu* m) { return m ? (int)m->scenes.size() : 0; }
+
+trq_scene* trq_mgpu_scene(trq_mgpu* m, int k) {
+    if (!m || k < 0 || k >= (int)m->scenes.size()) { trq::fail(TRQ_ERR_INVALID, "trq_mgpu_scene: index out of range"); return nullptr; }
+    return m->scenes[k];
+}
+
+int trq_mgpu_shard(const trq_mgpu* m, uint64_t n, int k, uint64_t* lo, uint64_t* hi) {
+    if (!m || !lo || !hi || k < 0 || k >= (int)m->scenes.size()) return trq::fail(TRQ_ERR_INVALID, "trq_mgpu_shard: bad argument");
+    const unsigned __int128 R = m->scenes.size();
+    *lo = (uint64_t)((unsigned __int128)n * (unsigned)k / R);
+    *hi = (uint64_t)((unsigned __int128)n * (unsigned)(k + 1) / R);
+    return TRQ_OK;
+}
+
+int trq_mgpu_trace(trq_mgpu* m, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits) {
+    if (!m) return trq::fail(TRQ_ERR_INVALID, "trq_mgpu_trace: NULL handle");
+    if (n == 0) return TRQ_OK;
+    if (!rays || !hits) return trq::fail(TRQ_ERR_INVALID, "trq_mgpu_trace: NULL rays/hits");
+    int first = TRQ_OK;
+    for (int k = 0; k < (int)m->scenes.size(); ++k) {           // queue every device's range ...
+        uint64_t lo, hi;
+        trq_mgpu_shard(m, n, k, &lo, &hi);
+        if (hi == lo) continue;
+        const int rc = trq_trace(m->scenes[k], rays + lo, hi - lo, flags | TRQ_HOST_PTRS | TRQ_HOST_ASYNC, hits + lo, nullptr);
+        if (rc != TRQ_OK && first == TRQ_OK) first = rc;
+    }
+    for (trq_scene* s : m->scenes) {                            // ... then wait for all of them
+        const int rc = trq_host_sync(s);
+        if (rc != TRQ_OK && first == TRQ_OK) first = rc;
+    }
+    return first;
+}
+
+int trq_mgpu_destroy(trq_mgpu* m) {
+    if (!m) return TRQ_OK;
+    for (trq_scene* s : m->scenes) trq_scene_destroy(s);
+    delete m;
+    return TRQ_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------
 // Memory-system probes for the roofline report ("no L2 figure is in MEASURED_PEAKS.json, so the
 // harness must measure it"): read-only 16-byte loads that bypass L1 (ld.global.cg) over a working set that fits in L2
 // (32 MB) or does not (2 GB), all SMs, best of five.

@@ -234,6 +234,45 @@ class Scene:
         return recs
 
 
+class MultiGpuScene:
+    """trq_mgpu_*: one process, one scene per device, host rays sharded contiguously across the devices (no collective)."""
+
+    def __init__(self, primitives, devices=None):
+        self.primitives = primitives
+        self._h = C.c_void_p(None)
+        d = primitives.desc()
+        if devices is None:
+            check(lib.trq_mgpu_create(C.byref(d), None, 0, C.byref(self._h)), "trq_mgpu_create")
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            check(lib.trq_mgpu_create(C.byref(d), arr, len(devices), C.byref(self._h)), "trq_mgpu_create")
+        self.n_devices = lib.trq_mgpu_device_count(self._h)
+
+    def shard(self, n, k):
+        lo, hi = C.c_uint64(0), C.c_uint64(0)
+        check(lib.trq_mgpu_shard(self._h, n, k, C.byref(lo), C.byref(hi)), "trq_mgpu_shard")
+        return lo.value, hi.value
+
+    def hit(self, rays, any=False, out=None, sort=False):
+        """numpy `ray_dtype` array -> numpy `hit_dtype` array (pinned buffers make the copies asynchronous)."""
+        rays = np.ascontiguousarray(rays)
+        hits = out if out is not None else np.empty(rays.size, dtype=L.hit_dtype)
+        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
+        check(lib.trq_mgpu_trace(self._h, rays.ctypes.data, rays.size, flags, hits.ctypes.data), "trq_mgpu_trace")
+        return hits
+
+    def hit_ptr(self, rays_ptr, n, hits_ptr, any=False, sort=False):
+        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
+        check(lib.trq_mgpu_trace(self._h, rays_ptr, n, flags, hits_ptr), "trq_mgpu_trace")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.trq_mgpu_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    __del__ = close
+
+
 def hits_to_numpy(hits):
     """torch (n, 8) float32 hit tensor -> numpy structured `hit_dtype` array (host copy)."""
     return hits.detach().cpu().numpy().view(L.hit_dtype).reshape(-1)
