@@ -168,3 +168,14 @@ def test_tree_equals_reference_builder_live(built, reference_builder):
         lv["mini"], lv["maxi"] = lo, lo + rng.integers(0, 3, (n, 3)).astype(np.float32)
         lv["pType"], lv["pIndex"] = L.TRIANGLE, np.arange(n)
         assert_same_tree(build_with_product(lv), reference_builder.build_tree(lv), f"lattice boxes n={n}")
+
+
+def test_c3_tree_equals_reference_builder(built, reference_builder):
+    """BASELINE C3 at full size: the 1.0 M-triangle scene's tree (built by the product builder inside the harness) is the
+    tree the reference's own BVH::buildTree makes of the same leaves."""
+    prim = H.scene_c3(2)
+    n = prim.nTri
+    assert n > 1_000_000 and prim.bvhList.size == 2 * n - 1
+    leaves = prim.bvhList[1:n + 1].copy()
+    leaves["parent"] = 0
+    assert_same_tree(prim.bvhList, reference_builder.build_tree(leaves), "C3")
