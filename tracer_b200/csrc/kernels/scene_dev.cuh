@@ -48,6 +48,7 @@ struct SceneDev {
     const float4*    nodes;     // 4 per interior node
     const float4*    tris;      // 3 per triangle leaf
     const float4*    sph;       // 2 per sphere leaf
+    const float4*    triN;      // 4 per triangle leaf (same slot as tris): {n0, leafNode} {n1, pIndex} {n2, 0} {pad}
     uint32_t         rootRef;
     float            rootMin[3], rootMax[3];
     uint32_t         nNode;

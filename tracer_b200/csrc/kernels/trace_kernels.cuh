@@ -168,6 +168,7 @@ struct TraceParams {
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
+    uint32_t       fused;          // triangle-only scene: write final trq_hit records at retirement (no resolve pass)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -297,11 +298,32 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         if (pending) {
             const uint32_t best = cold[COLD_BEST * TRQ_BLOCK];
             const bool hit = (range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) && best != 0xffffffffu;   // Render.hh:251
-            // triangle / sphere hits carry the ray direction (aux word = d.x) so that resolve_hits_kernel does not
-            // have to read the ray again for the front-face test
-            store_compact(P.hits, cold[COLD_RAY * TRQ_BLOCK], hit, range_y, best,
-                          coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK],
-                          coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
+            if (P.fused) {
+                // triangle-only scene: `best` is the triangle slot; finish the record here (Triangle.hh:73-82: interpolated
+                // normal, checkFace) and write the final trq_hit -- no resolve pass over the batch afterwards
+                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                if (hit) {
+                    const float4* np = S.triN + (size_t)best * 4u;
+                    float4 q0, q1;
+                    ldg8(np, q0, q1);
+                    const float4 q2 = ldg4(np + 2);
+                    const float u = coldf[COLD_U * TRQ_BLOCK], v = coldf[COLD_V * TRQ_BLOCK];
+                    const float w = fsub(fsub(1.0f, u), v);
+                    const f3 gn = add3(add3(scale3(make_f3(q1.x, q1.y, q1.z), u), scale3(make_f3(q2.x, q2.y, q2.z), v)),
+                                       scale3(make_f3(q0.x, q0.y, q0.z), w));
+                    const f3 d = make_f3(__uint_as_float(cold[COLD_AUX * TRQ_BLOCK]), coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
+                    const uint32_t front = front_face(d, gn) ? TRQ_HIT_FLAG_FRONT : 0u;
+                    o0 = make_float4(range_y, __uint_as_float((uint32_t)TRQ_TRIANGLE), q1.w, q0.w);
+                    o1 = make_float4(u, v, __uint_as_float(19u), __uint_as_float(TRQ_HIT_FLAG_HIT | front));
+                }
+                stg8(P.hits + cold[COLD_RAY * TRQ_BLOCK], o0, o1);
+            } else {
+                // triangle / sphere hits carry the ray direction (aux word = d.x) so that resolve_hits_kernel does not
+                // have to read the ray again for the front-face test
+                store_compact(P.hits, cold[COLD_RAY * TRQ_BLOCK], hit, range_y, best,
+                              coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK],
+                              coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
+            }
             pending = false;
         }
     };
@@ -427,7 +449,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 }
                 if (h) {
                     range_y = t;
-                    cold[COLD_BEST * TRQ_BLOCK] = leaf;
+                    cold[COLD_BEST * TRQ_BLOCK] = P.fused ? TRQ_REF_INDEX(cur) : leaf;
                     coldf[COLD_U * TRQ_BLOCK] = u; coldf[COLD_V * TRQ_BLOCK] = v;
                     cold[COLD_AUX * TRQ_BLOCK] = (kind == REF_SQUARE || kind == REF_CUBE) ? a : __float_as_uint(ray.d.x);
                 }
@@ -577,7 +599,7 @@ __global__ void __launch_bounds__(256)
 pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ ref, uint32_t nNode,
                   const RefVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
                   const RefSphere* __restrict__ spheres,
-                  float4* __restrict__ nodes, float4* __restrict__ tris, float4* __restrict__ sph) {
+                  float4* __restrict__ nodes, float4* __restrict__ tris, float4* __restrict__ sph, float4* __restrict__ triN) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nNode) return;
     const uint32_t my = ref[i];
@@ -599,6 +621,13 @@ pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ r
         out[0] = make_float4(v0.x, v0.y, v0.z, __uint_as_float(i));
         out[1] = make_float4(e1.x, e1.y, e1.z, 0.0f);
         out[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+        // what a finished triangle hit needs beyond (t, u, v): the vertex normals for checkFace, and its ids
+        const f3 n0 = ld3(verts[idx[3 * p]].n), n1 = ld3(verts[idx[3 * p + 1]].n), n2 = ld3(verts[idx[3 * p + 2]].n);
+        float4* on = triN + (size_t)slot * 4u;
+        on[0] = make_float4(n0.x, n0.y, n0.z, __uint_as_float(i));
+        on[1] = make_float4(n1.x, n1.y, n1.z, __uint_as_float(p));
+        on[2] = make_float4(n2.x, n2.y, n2.z, 0.0f);
+        on[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     } else if (kind == REF_SPHERE) {
         const RefSphere* s = &spheres[bvh[i].pIndex];
         float4* out = sph + (size_t)slot * 2u;

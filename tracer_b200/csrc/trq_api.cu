@@ -74,6 +74,8 @@ struct trq_scene {
     float4* d_nodes = nullptr;
     float4* d_tris = nullptr;
     float4* d_sph = nullptr;
+    float4* d_triN = nullptr;
+    bool allTriangles = false;    // every leaf is a triangle: the trace kernel finishes its own records (no resolve pass)
     SceneDev dev{};
     uint32_t stackDepth = 1;
     size_t traceSmem = 0;
@@ -104,7 +106,7 @@ void free_scene(trq_scene* s) {
     if (!s) return;
     cudaFree(s->d_spheres); cudaFree(s->d_squares); cudaFree(s->d_cubes);
     cudaFree(s->d_verts); cudaFree(s->d_idx); cudaFree(s->d_bvh);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_triN);
     cudaFree(s->d_counters);
     if (s->scratchPool) cudaMemPoolDestroy(s->scratchPool);
     for (int b = 0; b < kStageBufs; ++b) {
@@ -199,6 +201,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     }
     const bool any = (flags & TRQ_TRACE_ANY) != 0;
     unsigned long long* usedCounter = nullptr;
+    bool fused = false;
     cudaEvent_t* prof = nullptr;
     if (s->profile) {
         prof = s->evProf[s->profHead % kProfRing];
@@ -235,10 +238,14 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         // queue heads are zero at creation and re-zeroed by the resolve kernel that follows each trace on the stream
         unsigned long long* counter = s->d_counters + (s->counterNext.fetch_add(1) % kCounterRing);
         usedCounter = counter;
+        // triangle-only scene (and no peer gather): the trace kernel writes final records, there is no resolve pass
+        static const int fusedEnv = [] { const char* e = getenv("TRQ_FUSED_RESOLVE"); return e ? atoi(e) : 1; }();
+        fused = s->allTriangles && !gather && fusedEnv != 0;
+        if (fused) TRQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
         TraceParams P;
         P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
         P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
-        P.order = nullptr; P.nPtr = nPtr;
+        P.order = nullptr; P.nPtr = nPtr; P.fused = fused ? 1u : 0u;
         if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));      // the ordering pass is part of the timed traversal
         // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
         // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
@@ -264,7 +271,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         if (scratch) TRQ_CUDA(cudaFreeAsync(scratch, st));
     }
     if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
-    {
+    if (!fused) {
         const unsigned block = 256;
         const uint64_t grid = n ? (n + block - 1) / block : 1;
         if (gather) resolve_hits_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr, usedCounter, *gather);
@@ -438,13 +445,15 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes));
     if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes));
     if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes));
+    const size_t triNBytes = (size_t)info.nTri * 64;
+    if (triNBytes && cudaMalloc((void**)&s->d_triN, triNBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(triangle normals %zu B) failed", triNBytes));
     if (cudaMalloc((void**)&s->d_counters, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(counters) failed"));
     if (cudaMemset(s->d_counters, 0, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMemset(counters) failed"));
 
     {
         const unsigned block = 256, grid = (d->nNode + block - 1) / block;
         pack_scene_kernel<<<grid, block>>>(s->d_bvh, d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres,
-                                           s->d_nodes, s->d_tris, s->d_sph);
+                                           s->d_nodes, s->d_tris, s->d_sph, s->d_triN);
         g_launches++;
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "pack_scene_kernel failed: %s", cudaGetErrorString(e)));
@@ -454,7 +463,8 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     const RefBVH* N = (const RefBVH*)d->bvhList;
     s->dev.spheres = s->d_spheres; s->dev.squares = s->d_squares; s->dev.cubes = s->d_cubes;
     s->dev.verts = s->d_verts; s->dev.idx = s->d_idx; s->dev.bvh = s->d_bvh;
-    s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.sph = s->d_sph;
+    s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.sph = s->d_sph; s->dev.triN = s->d_triN;
+    s->allTriangles = info.nTri > 0 && info.nTri == info.nLeaf;
     s->dev.rootRef = ref[0];
     for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = N[0].bBOX.mini[k]; s->dev.rootMax[k] = N[0].bBOX.maxi[k]; }
     s->dev.nNode = d->nNode;
@@ -487,7 +497,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     info.bytesReferenceLayout = (uint64_t)d->nSphere * sizeof(RefSphere) + (uint64_t)d->nSquare * sizeof(RefSquare) +
                                 (uint64_t)d->nCube * sizeof(RefCube) + (uint64_t)d->nVert * sizeof(RefVertex) +
                                 (uint64_t)d->nTri * 12 + (uint64_t)d->nNode * sizeof(RefBVH);
-    info.bytesPacked = nodeBytes + triBytes + sphBytes;
+    info.bytesPacked = nodeBytes + triBytes + sphBytes + triNBytes;
     info.device = device;
     s->info = info;
     *out = s;
