@@ -168,7 +168,6 @@ struct TraceParams {
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
-    uint32_t       fused;          // triangle-only scene: write final trq_hit records at retirement (no resolve pass)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -274,7 +273,9 @@ enum : uint32_t { COLD_TEST_T = 0, COLD_BEST, COLD_U, COLD_V, COLD_AUX, COLD_RAY
 __device__ unsigned long long g_stats[8];
 #endif
 
-template <bool ANY>
+// FUSED (triangle-only scenes): a retiring ray's final trq_hit is written by this kernel; otherwise a compact result is
+// written and resolve_hits_kernel finishes it.
+template <bool ANY, bool FUSED>
 __global__ void __launch_bounds__(TRQ_BLOCK, TRQ_MIN_BLOCKS)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
     extern __shared__ uint32_t smem_u32[];
@@ -298,7 +299,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         if (pending) {
             const uint32_t best = cold[COLD_BEST * TRQ_BLOCK];
             const bool hit = (range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) && best != 0xffffffffu;   // Render.hh:251
-            if (P.fused) {
+            if (FUSED) {
                 // triangle-only scene: `best` is the triangle slot; finish the record here (Triangle.hh:73-82: interpolated
                 // normal, checkFace) and write the final trq_hit -- no resolve pass over the batch afterwards
                 float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
@@ -449,7 +450,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 }
                 if (h) {
                     range_y = t;
-                    cold[COLD_BEST * TRQ_BLOCK] = P.fused ? TRQ_REF_INDEX(cur) : leaf;
+                    cold[COLD_BEST * TRQ_BLOCK] = FUSED ? TRQ_REF_INDEX(cur) : leaf;
                     coldf[COLD_U * TRQ_BLOCK] = u; coldf[COLD_V * TRQ_BLOCK] = v;
                     cold[COLD_AUX * TRQ_BLOCK] = (kind == REF_SQUARE || kind == REF_CUBE) ? a : __float_as_uint(ray.d.x);
                 }

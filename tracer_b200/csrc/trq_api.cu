@@ -79,7 +79,7 @@ struct trq_scene {
     SceneDev dev{};
     uint32_t stackDepth = 1;
     size_t traceSmem = 0;
-    int blocksPerSM[2] = {0, 0};  // resident trace_packed_kernel CTAs per SM: [closest-hit, any-hit]
+    int blocksPerSM[2][2] = {};   // resident trace_packed_kernel CTAs per SM: [closest-hit, any-hit][compact result, fused finish]
     // stream-ordered scratch for TRQ_SORT_RAYS: a private pool that keeps its memory across synchronisations
     // (the device's default pool hands it back at every sync and re-maps 64 MB on the next sorted launch)
     cudaMemPool_t scratchPool = nullptr;
@@ -230,7 +230,10 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         }();
         static const int blocksPerSMOverride =[] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
         const size_t smem = s->traceSmem;
-        int perSM = s->blocksPerSM[any ? 1 : 0];                                 // queried once, in trq_scene_create
+        // triangle-only scene (and no peer gather): the trace kernel writes final records, there is no resolve pass
+        static const int fusedEnv = [] { const char* e = getenv("TRQ_FUSED_RESOLVE"); return e ? atoi(e) : 1; }();
+        fused = s->allTriangles && !gather && fusedEnv != 0;
+        int perSM = s->blocksPerSM[any ? 1 : 0][fused ? 1 : 0];                  // queried once, in trq_scene_create
         if (blocksPerSMOverride > 0 && blocksPerSMOverride < perSM) perSM = blocksPerSMOverride;
         uint64_t grid = (uint64_t)perSM * (uint64_t)s->numSMs;             // persistent: a multiple of the SM count
         const uint64_t need = (n + TRQ_BLOCK - 1) / TRQ_BLOCK;
@@ -238,14 +241,11 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         // queue heads are zero at creation and re-zeroed by the resolve kernel that follows each trace on the stream
         unsigned long long* counter = s->d_counters + (s->counterNext.fetch_add(1) % kCounterRing);
         usedCounter = counter;
-        // triangle-only scene (and no peer gather): the trace kernel writes final records, there is no resolve pass
-        static const int fusedEnv = [] { const char* e = getenv("TRQ_FUSED_RESOLVE"); return e ? atoi(e) : 1; }();
-        fused = s->allTriangles && !gather && fusedEnv != 0;
-        if (fused) TRQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+        if (fused) TRQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));   // no resolve kernel to re-zero it
         TraceParams P;
         P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
         P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
-        P.order = nullptr; P.nPtr = nPtr; P.fused = fused ? 1u : 0u;
+        P.order = nullptr; P.nPtr = nPtr;
         if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));      // the ordering pass is part of the timed traversal
         // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
         // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
@@ -265,8 +265,10 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             g_launches += 3;
             P.order = order;
         }
-        if (any) trace_packed_kernel<true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
-        else     trace_packed_kernel<false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
+        if (any) { if (fused) trace_packed_kernel<true, true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
+                   else       trace_packed_kernel<true, false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P); }
+        else     { if (fused) trace_packed_kernel<false, true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
+                   else       trace_packed_kernel<false, false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P); }
         g_launches++;
         if (scratch) TRQ_CUDA(cudaFreeAsync(scratch, st));
     }
@@ -483,14 +485,16 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     s->traceSmem = ((size_t)s->stackDepth + COLD_WORDS) * TRQ_BLOCK * sizeof(uint32_t);
     {
         cudaError_t e = cudaSuccess;
-        if (s->traceSmem > 48 * 1024) {
-            e = cudaFuncSetAttribute(trace_packed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->traceSmem);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(trace_packed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->traceSmem);
-        }
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocksPerSM[0], trace_packed_kernel<false>, TRQ_BLOCK, s->traceSmem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocksPerSM[1], trace_packed_kernel<true>, TRQ_BLOCK, s->traceSmem);
+        const void* variants[2][2] = {{(const void*)trace_packed_kernel<false, false>, (const void*)trace_packed_kernel<false, true>},
+                                      {(const void*)trace_packed_kernel<true, false>, (const void*)trace_packed_kernel<true, true>}};
+        for (int a = 0; a < 2; ++a)
+            for (int f = 0; f < 2; ++f) {
+                if (e == cudaSuccess && s->traceSmem > 48 * 1024)
+                    e = cudaFuncSetAttribute(variants[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->traceSmem);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocksPerSM[a][f], variants[a][f], TRQ_BLOCK, s->traceSmem);
+            }
         if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel occupancy query failed: %s", cudaGetErrorString(e)));
-        if (s->blocksPerSM[0] < 1 || s->blocksPerSM[1] < 1)
+        if (s->blocksPerSM[0][0] < 1 || s->blocksPerSM[0][1] < 1 || s->blocksPerSM[1][0] < 1 || s->blocksPerSM[1][1] < 1)
             return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->traceSmem));
     }
 
