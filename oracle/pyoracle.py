@@ -211,6 +211,15 @@ class Reference:
         self.lib.ref_cosine_sample_hemisphere(C.c_void_p(u.ctypes.data), C.c_void_p(out.ctypes.data))
         return out
 
+    def square_sample(self, square, uu, pos):
+        """Square::sample (Square.hh:40-58) -> (lsr.p, lsr.n)."""
+        sq = np.ascontiguousarray(square).reshape(1)
+        u, p = _fp(uu), _fp(pos)
+        po, no = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        self.lib.ref_square_sample(C.c_void_p(sq.ctypes.data), C.c_void_p(u.ctypes.data), C.c_void_p(p.ctypes.data),
+                                   C.c_void_p(po.ctypes.data), C.c_void_p(no.ctypes.data))
+        return po, no
+
     def pcg32(self, initstate, initseq, n):
         """pcg32_srandom_r + n x pcg32_random_r / randomF (Random.metal:3-26) -> (uint32 array, float32 array)."""
         u = np.zeros(n, dtype=np.uint32)

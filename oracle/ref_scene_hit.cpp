@@ -264,6 +264,17 @@ void ref_cosine_sample_hemisphere(const float* u, float* out) {
 float ref_next_float_up(float v) { return NextFloatUp(v); }
 float ref_next_float_down(float v) { return NextFloatDown(v); }
 
+// Square::sample (Square.hh:40-58): the light sample of the NEE shadow ray (Render.metal:313-323)
+void ref_square_sample(const void* square, const float* u2, const float* pos3, float* p_out, float* n_out) {
+    const Square* sq = reinterpret_cast<const Square*>(square);
+    LightSampleRecord lsr;
+    float2 uu(u2[0], u2[1]);
+    float3 pos(pos3[0], pos3[1], pos3[2]);
+    sq->sample(uu, pos, lsr);
+    p_out[0] = lsr.p.x; p_out[1] = lsr.p.y; p_out[2] = lsr.p.z;
+    n_out[0] = lsr.n.x; n_out[1] = lsr.n.y; n_out[2] = lsr.n.z;
+}
+
 // PCG32 as the reference's kernels run it (Random.metal:3-26) and RandomSampler::sample2D (RandomSampler.hh:16-21)
 void ref_pcg32_fill(uint64_t initstate, uint64_t initseq, uint32_t n, uint32_t* u32_out, float* f32_out) {
     pcg32_t a, b;

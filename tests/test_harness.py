@@ -52,9 +52,10 @@ def test_bounce_rays_follow_the_reference_spawn(reference, port):
         uu = H.pcg32_floats(7 + int(src[k]), 1, 2)
         nx, ny = reference.coordinate_system(rec["sn"])
         wi = reference.cosine_sample_hemisphere(uu)
-        want = nx * wi[0] + ny * wi[1] + rec["sn"] * wi[2]
-        want = want / np.linalg.norm(want)
-        assert np.allclose(rays["d"][k], want, atol=2e-6)
+        want = ((nx * wi[0]).astype(np.float32) + (ny * wi[1]).astype(np.float32)).astype(np.float32)
+        want = (want + (rec["sn"] * wi[2]).astype(np.float32)).astype(np.float32)                             # stw * wi  :475
+        _, want = reference.ray_ctor(rays["o"][k], want)                                                      # ray.update normalises
+        assert np.array_equal(bits(rays["d"][k]), bits(want)), k                                              # host producer: bit for bit
         assert np.dot(rays["d"][k], rec["sn"]) >= -1e-6                                                        # into the hemisphere of sn
 
 
@@ -69,6 +70,32 @@ def test_shadow_rays_point_at_the_lights(reference):
     on_b = np.abs(end[:, 0] + 300) < 0.5
     assert (on_a | on_b).all() and on_a.any() and on_b.any()
     assert np.allclose(np.linalg.norm(rays["d"], axis=1), 1.0, atol=1e-6)
+
+
+def test_shadow_rays_follow_the_reference_spawn(reference):
+    """Render.metal:313-337 composed from the reference's own pieces (sample2D, offset_ray, Square::sample, the Ray ctor):
+    the producer's shadow rays are those rays bit for bit."""
+    f32 = np.float32
+    prim = H.scene_reference_cornell()
+    first = reference.trace(prim, H.cornell_camera_rays(48, 27))
+    la, lb = prim.squareList[5], prim.squareList[6]
+    rays, src = H.shadow_rays(first, prim.squareList[5:6], prim.squareList[6:7], seed_base=3)
+    picked = [0, 0]
+    for k in range(0, rays.size, 23):
+        rec = first[src[k]]
+        u, f = reference.pcg32(3 + int(src[k]), 1, 3)
+        origin = reference.offset_ray(rec["p"], rec["sn"])                       # :316
+        which = 0 if f[2] < f32(0.5) else 1                                      # :319-323
+        picked[which] += 1
+        lp, _ = reference.square_sample(la if which == 0 else lb, f[:2], origin)
+        dirv = (lp - origin).astype(np.float32)                                  # :325
+        _, nor = reference.ray_ctor(origin, dirv)                                # normalize(_dir)  :326
+        _, d = reference.ray_ctor(origin, nor)                                   # Ray(_origin, _nor) normalises again  :335
+        dis = np.sqrt(f32(f32(dirv[0] * dirv[0] + dirv[1] * dirv[1]) + dirv[2] * dirv[2]), dtype=np.float32)   # length(_dir)  :334
+        assert np.array_equal(bits(rays["o"][k]), bits(origin)), k
+        assert np.array_equal(bits(rays["d"][k]), bits(d)), k
+        assert bits(rays["tmax"][k:k + 1])[0] == bits(np.array([dis], dtype=np.float32))[0], k
+    assert picked[0] > 0 and picked[1] > 0
 
 
 def test_random_rays_and_soup_are_deterministic_and_shardable():
