@@ -211,6 +211,14 @@ class Reference:
         self.lib.ref_cosine_sample_hemisphere(C.c_void_p(u.ctypes.data), C.c_void_p(out.ctypes.data))
         return out
 
+    def cast_ray(self, cam18, s, t, len_radius=0.0, seed=1, seq=1):
+        """castRay (Camera.hh:59-69) -> (origin, direction)."""
+        c = _fp(cam18)
+        o, d = np.zeros(3, dtype=np.float32), np.zeros(3, dtype=np.float32)
+        self.lib.ref_cast_ray(C.c_void_p(c.ctypes.data), C.c_float(len_radius), C.c_float(s), C.c_float(t), C.c_uint64(seed), C.c_uint64(seq),
+                              C.c_void_p(o.ctypes.data), C.c_void_p(d.ctypes.data))
+        return o, d
+
     def square_sample(self, square, uu, pos):
         """Square::sample (Square.hh:40-58) -> (lsr.p, lsr.n)."""
         sq = np.ascontiguousarray(square).reshape(1)

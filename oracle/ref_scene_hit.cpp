@@ -35,7 +35,6 @@
 
 // Blank out the shading-side headers Render.hh:5-22 would pull in (not on the hot path). Random.hh stays: it only
 // declares, and its pcg32_t {state, inc} (Random.hh:6-12) is what toRNG / exRNG (Render.hh:96-120) are written against.
-#define Camera_h
 #define Light_h
 #define Spectrum_h
 #define Medium_h
@@ -263,6 +262,25 @@ void ref_cosine_sample_hemisphere(const float* u, float* out) {
 }
 float ref_next_float_up(float v) { return NextFloatUp(v); }
 float ref_next_float_down(float v) { return NextFloatDown(v); }
+
+// castRay (Camera.hh:59-69) with a camera given as MakeCamera's outputs {lookFrom, u, v, vertical, horizontal, cornerLowLeft}
+// and lenRadius; the sampler is seeded (seed, seq) because castRay draws sampleUnitInDisk() even when lenRadius is 0.
+void ref_cast_ray(const float* cam18, float lenRadius, float s, float t, uint64_t seed, uint64_t seq, float* origin, float* direction) {
+    Camera c;
+    c.lookFrom = float3(cam18[0], cam18[1], cam18[2]);
+    c.u = float3(cam18[3], cam18[4], cam18[5]);
+    c.v = float3(cam18[6], cam18[7], cam18[8]);
+    c.vertical = float3(cam18[9], cam18[10], cam18[11]);
+    c.horizontal = float3(cam18[12], cam18[13], cam18[14]);
+    c.cornerLowLeft = float3(cam18[15], cam18[16], cam18[17]);
+    c.lenRadius = lenRadius;
+    pcg32_t r;
+    pcg32_srandom_r(&r, seed, seq);
+    RandomSampler rs { &r };
+    Ray ray = castRay(&c, s, t, &rs);
+    origin[0] = ray.origin.x; origin[1] = ray.origin.y; origin[2] = ray.origin.z;
+    direction[0] = ray.direction.x; direction[1] = ray.direction.y; direction[2] = ray.direction.z;
+}
 
 // Square::sample (Square.hh:40-58): the light sample of the NEE shadow ray (Render.metal:313-323)
 void ref_square_sample(const void* square, const float* u2, const float* pos3, float* p_out, float* n_out) {

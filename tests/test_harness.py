@@ -41,6 +41,19 @@ def test_camera_rays_are_reference_rays(reference):
     assert np.allclose(d2, rays["d"][5], atol=1e-7)
 
 
+def test_camera_rays_are_castray_bit_for_bit(reference, reference_setup):
+    """trqh_gen_camera_rays == the reference's castRay (Camera.hh:59-69) over the camera its prepareCamera builds
+    (Tracer.mm:371-411), with s = x / W, t = y / H (Render.metal:523-524): origins and directions bit for bit."""
+    W, Hh = 64, 36
+    rays = H.cornell_camera_rays(W, Hh)
+    cam = reference_setup.prepare_camera(W, Hh)
+    for y in range(0, Hh, 5):
+        for x in range(0, W, 7):
+            o, d = reference.cast_ray(cam, np.float32(x) / np.float32(W), np.float32(y) / np.float32(Hh), seed=x + 1, seq=y + 1)
+            k = y * W + x
+            assert np.array_equal(bits(rays["o"][k]), bits(o)) and np.array_equal(bits(rays["d"][k]), bits(d)), (x, y)
+
+
 def test_bounce_rays_follow_the_reference_spawn(reference, port):
     prim = H.scene_reference_cornell()
     first = reference.trace(prim, H.cornell_camera_rays(48, 27))
