@@ -2,7 +2,7 @@
 //
 // Mirrors what RT_Metal's host does around the hot path (AAPLRenderer.mm:546-624, Render.metal:523-532):
 // make per-triangle leaves, build the BVH, upload the scene, cast a small grid of camera rays, trace
-// closest-hit and any-hit, expand the hit records. Build (from the repo root):
+// closest-hit and any-hit, expand the hit records, then shard the same batch over every visible GPU. Build (from the repo root):
 //   g++ -std=c++17 -O2 -Iinclude examples/host_cpp/trace_example.cpp -Ltracer_b200 -ltracer_rq \
 //       -Wl,-rpath,$PWD/tracer_b200 -o examples/host_cpp/trace_example
 // Exit code 0 on success, 3 when there is no CUDA device (there is no CPU fallback), 1 on any other error.
@@ -76,5 +76,14 @@ int main() {
                 rays.size(), recs[(H / 2) * W + W / 2].p[0], recs[(H / 2) * W + W / 2].p[1], recs[(H / 2) * W + W / 2].p[2],
                 recs[(H / 2) * W + W / 2].t);
     CHECK(trq_scene_destroy(scene));
+
+    // the same batch sharded over every visible GPU from this one process (one scene per device, no collective)
+    trq_mgpu* all = nullptr;
+    CHECK(trq_mgpu_create(&desc, nullptr, 0, &all));
+    std::vector<trq_hit> sharded(rays.size());
+    CHECK(trq_mgpu_trace(all, rays.data(), rays.size(), 0, sharded.data()));
+    if (std::memcmp(sharded.data(), hits.data(), hits.size() * sizeof(trq_hit)) != 0) { std::fprintf(stderr, "sharded trace differs\n"); return 1; }
+    std::printf("sharded over %d device(s): identical\n", trq_mgpu_device_count(all));
+    CHECK(trq_mgpu_destroy(all));
     return nHit > 0 ? 0 : 1;
 }
