@@ -11,7 +11,10 @@
 //                           ORDER per ray is exactly the reference's: near child first by hit_t's t,
 //                           ties to the right child, the far child decided at first arrival and never
 //                           re-tested, including the "select the missed child" quirk of Render.hh:174.
-//   resolve_hits_kernel     compact result -> trq_hit (pType, pIndex, front, material, sphere uv)
+//                           FUSED variant (triangle-only scenes): writes the final trq_hit when a ray retires.
+//   resolve_hits_kernel     compact result -> trq_hit (pType, pIndex, front, material, sphere uv) for scenes with
+//                           sphere / square / cube leaves; GATHER variant also stores the record to every peer GPU
+//   sort_*_kernel           optional ordering of the work queue (TRQ_SORT_RAYS)
 //   expand_hits_kernel      trq_hit -> HitRecord fields (p, gn, sn, uv, f, material)
 #pragma once
 #include <cfloat>
