@@ -150,3 +150,33 @@ def test_rng_state_texture_two_waves(cornell):
     w2s = w2[np.argsort(ws2, kind="stable")]
     assert np.array_equal(bits(g2["o"]), bits(w2s["o"])) and np.array_equal(bits(g2["d"]), bits(w2s["d"]))
     assert (tex_h != begun).any(axis=1).sum() == n1                      # exactly the pixels that hit drew numbers
+
+
+def test_device_wavefront_triangle_only_scene(built, port):
+    """The same wavefront on a triangle-only scene (C2), where the trace kernel finishes its own records (no resolve
+    pass): indirect batch sizes, closest and any-hit, against the oracle."""
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H, hits_to_numpy
+    prim = H.scene_c2()
+    scene = Scene(prim, 0)
+    assert scene.info["nTri"] == scene.info["nLeaf"]
+    W, Hh = 320, 180
+    r0 = scene.cast_rays((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)), W, Hh)
+    h0 = scene.hit(r0)
+    r1, s1, c1 = scene.spawn_bounce(r0, h0, seed_base=5)
+    h1 = scene.hit_indirect(r1, c1)
+    a1 = scene.hit_indirect(r1, c1, any=True)
+    s_h1 = scene.hit_indirect(r1, c1, sort=True)
+    torch.cuda.synchronize()
+    n1 = int(c1.item())
+    assert 0 < n1 < W * Hh
+    assert torch.equal(s_h1[:n1].view(torch.int32), h1[:n1].view(torch.int32))
+    for rays_t, hits_t, n, any_hit in ((r0, h0, W * Hh, False), (r1, h1, n1, False), (r1, a1, n1, True)):
+        rays = _np_rays(rays_t, n).copy()
+        got = hits_to_numpy(hits_t)[:n]
+        want = port.trace(prim, rays, any=any_hit, nthreads=8)["hits"]
+        for k in ("flags", "pType", "pIndex", "leafNode", "material"):
+            assert np.array_equal(got[k], want[k]), k
+        for k in ("t", "u", "v"):
+            assert np.array_equal(bits(got[k]), bits(want[k])), k
+    scene.close()
