@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define TRQ_VERSION 100  /* 0.1.0 */
+#define TRQ_VERSION 200  /* 0.2.0 */
 
 typedef enum trq_status {
     TRQ_OK            =  0,
@@ -90,6 +90,19 @@ typedef struct trq_hit {
     uint32_t flags;              /* TRQ_HIT_FLAG_* */
 } trq_hit;
 
+/* 16 B, opt-in (TRQ_HIT16): what a consumer needs to shade or to test occlusion, at half the bytes on every wire
+ * (PCIe D2H, NVLink gather). id = 0xffffffff on a miss, else  front << 31 | pType << 28 | pIndex  (pIndex < 2^28);
+ * t, u, v as in trq_hit. material and leafNode are not carried (material is a function of the primitive). */
+typedef struct trq_hit16 {
+    float    t;
+    uint32_t id;
+    float    u, v;
+} trq_hit16;
+#define TRQ_HIT16_MISS      0xffffffffu
+#define TRQ_HIT16_FRONT(id) ((id) >> 31)
+#define TRQ_HIT16_PTYPE(id) (((id) >> 28) & 7u)
+#define TRQ_HIT16_PINDEX(id) ((id) & 0x0fffffffu)
+
 /* 64 B. The HitRecord fields the query writes (for callers that shade). */
 typedef struct trq_hit_record {
     uint32_t hit;
@@ -110,7 +123,8 @@ typedef struct trq_scene_info_t {
     uint64_t bytesReferenceLayout;   /* device bytes of the six arrays as uploaded */
     uint64_t bytesPacked;            /* device bytes of the derived traversal layout */
     int32_t  device;
-    uint32_t pad;
+    uint32_t topNodes;           /* interior nodes numbered breadth-first at the front of the packed array: the block the
+                                    traversal kernel can stage in shared memory (top levels of the tree) */
 } trq_scene_info_t;
 
 /* trq_trace / trq_expand_hits flags */
@@ -121,6 +135,8 @@ typedef struct trq_scene_info_t {
                                        (correctness anchor / naive baseline) instead of the packed kernel */
 #define TRQ_SORT_RAYS        0x8u   /* hint: the batch is incoherent; the library may order the work queue by
                                        (origin cell, direction octant) first. Results are identical either way. */
+
+#define TRQ_HIT16            0x20u  /* `hits` is trq_hit16[n] (16-byte aligned) instead of trq_hit[n] */
 
 #define TRQ_HOST_ASYNC       0x10u  /* with TRQ_HOST_PTRS: return as soon as the copies and kernels are queued; the host
                                        buffers must stay valid (and should be pinned) until trq_host_sync() returns.
@@ -138,11 +154,22 @@ int  trq_scene_create(const trq_scene_desc* desc, int device, trq_scene** out);
 int  trq_scene_destroy(trq_scene* scene);
 int  trq_scene_info(const trq_scene* scene, trq_scene_info_t* info);
 
+/* Launch configurations of the traversal kernel (tuning knob; results are identical in all of them). A configuration is
+ * "CTA size x resident CTAs per SM", with or without the top levels of the tree staged in shared memory by a TMA bulk
+ * copy (names end in "true" / "false"). cfg < 0 selects the library's choice for this scene. TRQ_CFG=<n> in the
+ * environment overrides every scene (experiments). topNodesStaged (optional): how many interior nodes that
+ * configuration keeps in shared memory for this scene. */
+int  trq_kernel_config_count(void);
+const char* trq_kernel_config_name(int cfg);
+int  trq_scene_set_kernel_config(trq_scene* scene, int cfg, uint32_t* topNodesStaged);
+
 /* Scene::hit for n rays. Device pointers unless TRQ_HOST_PTRS; asynchronous on `stream`
- * (a cudaStream_t, NULL = default stream) for device pointers. Re-entrant across streams.
- * Device rays / hits must be 32-byte aligned (every record is moved with one 256-bit access). */
+ * (a cudaStream_t, NULL = default stream) for device pointers. Re-entrant across streams and host threads (any number
+ * of launches in flight on any number of streams; each draws its own work-queue head).
+ * `hits` is trq_hit[n], or trq_hit16[n] with TRQ_HIT16. Device rays / hits must be aligned to their record size
+ * (32 bytes; 16 for trq_hit16): every record is moved with one access. */
 int  trq_trace(trq_scene* scene, const trq_ray* rays, uint64_t n, uint32_t flags,
-               trq_hit* hits, void* stream);
+               void* hits, void* stream);
 
 /* Waits for every TRQ_HOST_ASYNC call issued on this scene. */
 int  trq_host_sync(trq_scene* scene);
@@ -215,14 +242,17 @@ int  trq_mgpu_destroy(trq_mgpu* m);
 
 /* ---- multi-GPU: hit gather through NVLink peer memory (one process per GPU, one node) -----------------------
  * Rays shard across ranks with no collective. A consumer that wants EVERY rank's hits whole
- * (the all-gather of trq_hit[N/R] of section 8e) gets them from the resolve kernel itself: each finished record is
- * stored into slot [rank] of every rank's buffer over NVLink, then (count, step) are published with system-scope
- * release stores -- no NCCL call, no second pass over the records.
+ * (the all-gather of trq_hit[N/R] of section 8e) gets them from the traversal kernel itself: as each ray retires, its
+ * finished record is stored into slot [rank] of every rank's buffer over NVLink -- the transfer runs under the
+ * traversal -- and the kernel's last CTA publishes (count, step) with system-scope release stores. No NCCL call, no
+ * second pass over the records.
  *   1. every rank: trq_gather_create -> 64-byte handle; exchange the handles (any transport, e.g. MPI /
  *      torch.distributed all_gather) into a world*64-byte array in rank order; trq_gather_connect.
- *   2. per step: trq_trace_gather(rays of this rank) then trq_gather_wait -> hitsAll[r*capacity + i], counts[r];
- *      both are asynchronous on `stream`; the buffers alternate between two parities, so the result of step k stays
- *      valid until this rank calls trq_trace_gather for step k+2. Every rank must call both every step.
+ *   2. per step: trq_trace_gather(rays of this rank) then trq_gather_wait -> hitsAll, counts[r]; rank r's records
+ *      start at byte r * capacity * 32 of hitsAll and are trq_hit, or trq_hit16 when the step was traced with
+ *      TRQ_HIT16 (same slot stride). Both calls are asynchronous on `stream`; the buffers rotate through three phases,
+ *      so the result of step k stays valid until this rank's trq_trace_gather for step k+2 EXECUTES (a peer cannot
+ *      reuse the phase before it has seen this rank finish step k+2). Every rank must call both every step.
  *   3. all ranks synchronise (barrier) before any of them calls trq_gather_destroy.
  * trq_gather_status (after synchronising the stream) reports a peer that never published (timeout 10 s,
  * TRQ_GATHER_TIMEOUT_MS) instead of hanging the GPU. */
@@ -232,7 +262,7 @@ int  trq_gather_create(trq_scene* scene, uint32_t rank, uint32_t world, uint64_t
                        void* handle /* TRQ_GATHER_HANDLE_BYTES */);
 int  trq_gather_connect(trq_gather* g, const void* handles /* world * TRQ_GATHER_HANDLE_BYTES, rank order */);
 int  trq_trace_gather(trq_scene* scene, trq_gather* g, const trq_ray* rays, uint64_t n, uint32_t flags, void* stream);
-int  trq_gather_wait(trq_gather* g, void* stream, const trq_hit** hitsAll, const uint64_t** counts);
+int  trq_gather_wait(trq_gather* g, void* stream, const void** hitsAll, const uint64_t** counts);
 int  trq_gather_status(trq_gather* g);
 int  trq_gather_destroy(trq_gather* g);
 

@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported(built):
         assert hasattr(lib, n), f"{n} declared in include/ but not exported by libtracer_rq.so"
     assert set(_lib.ABI_SYMBOLS) <= set(declared("tracer_rq.h"))
     assert set(_lib.HARNESS_SYMBOLS) <= set(declared("tracer_rq_harness.h"))
-    assert lib.trq_version() == 100
+    assert lib.trq_version() == 200
 
 
 def test_struct_sizes_match_header(built):

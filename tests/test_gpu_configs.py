@@ -1,0 +1,98 @@
+"""GPU: every launch configuration of the traversal kernel (CTA size x CTAs per SM, top of the tree staged in shared
+memory by a TMA bulk copy or not) and both record formats (trq_hit, trq_hit16) produce the oracle's results.
+
+The top-of-tree block is the first `topNodes` packed interior nodes in breadth-first order; a configuration stages a
+prefix of it, so the residency test inside the kernel is "index < topCount" (Render.hh:145-160 re-reads those levels
+from memory for every ray)."""
+import numpy as np
+import pytest
+
+from tracer_b200 import layout as L
+
+from test_gpu_parity import _torch, assert_hits_equal, gpu_trace
+
+pytestmark = pytest.mark.gpu
+
+
+def _configs():
+    from tracer_b200 import Scene
+    return list(enumerate(Scene.kernel_configs()))
+
+
+def test_every_configuration_matches_the_oracle(built, port):
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H
+    names = Scene.kernel_configs()
+    assert len(names) >= 2 and names[0].endswith("false") and any(n.endswith("true") for n in names)
+    soup = H.scene_soup(200000, seed=1, extent=0.01)
+    mixed = H.scene_reference_cornell()
+    cases = [(soup, H.random_rays(300000, seed=2), False), (soup, H.random_rays(100000, seed=3), True),
+             (mixed, H.cornell_camera_rays(320, 180), False),
+             (mixed, H.random_rays(100000, seed=5, lo=(-245, 0, 0), hi=(800, 555, 555)), True)]
+    wants = [port.trace(p, r, any=a, nthreads=8)["hits"] for p, r, a in cases]
+    staged_any = False
+    for prim in (soup, mixed):
+        scene = Scene(prim, 0)
+        assert 0 < scene.info["topNodes"] <= min(2047, scene.info["nInterior"])
+        for c, name in enumerate(names):
+            try:
+                staged = scene.set_kernel_config(c)
+            except Exception:                                  # a configuration may not fit a deep tree
+                continue
+            assert (staged > 0) == name.endswith("true"), (name, staged)
+            staged_any |= staged > 0
+            for (p, rays, any_hit), want in zip(cases, wants):
+                if p is prim:
+                    assert_hits_equal(gpu_trace(scene, rays, any_hit), want, f"cfg {name}")
+        scene.close()
+    assert staged_any
+
+
+def test_hit16_is_the_packed_form_of_trq_hit(built, port):
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H, rays_to_torch
+    for prim, rays in ((H.scene_reference_cornell(), H.cornell_camera_rays(320, 180)),
+                       (H.scene_soup(100000, seed=4, extent=0.02), H.random_rays(200000, seed=6))):
+        scene = Scene(prim, 0)
+        d = rays_to_torch(rays, "cuda:0")
+        for any_hit in (False, True):
+            full = scene.hit(d, any=any_hit).cpu().numpy().view(L.hit_dtype).reshape(-1)
+            for c in range(len(Scene.kernel_configs())):
+                try:
+                    scene.set_kernel_config(c)
+                except Exception:
+                    continue
+                small = scene.hit(d, any=any_hit, hit16=True)
+                assert small.shape == (rays.size, 4)
+                got = small.cpu().numpy().view(L.hit16_dtype).reshape(-1)
+                assert np.array_equal(got.view(np.uint8), L.pack_hit16(full).view(np.uint8)), (c, any_hit)
+            scene.set_kernel_config(-1)
+        # host-pointer path with 16-byte records (half the D2H bytes)
+        host = scene.hit(rays, hit16=True)
+        assert host.dtype == L.hit16_dtype
+        want = port.trace(prim, rays, nthreads=8)["hits"]
+        assert np.array_equal(host["id"], L.pack_hit16(want)["id"])
+        assert np.array_equal(host["t"].view(np.uint32), want["t"].view(np.uint32))
+        scene.close()
+
+
+def test_host_path_tapered_chunks(built):
+    """TRQ_HOST_PTRS cuts a large batch into chunks that ramp up and down (1/8, 1/4, 1/2, 1 ... 1, 1/2, 1/4, 1/8);
+    every ray must land at its own index for sizes around the chunk boundaries."""
+    import os
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H, rays_to_torch
+    prim = H.scene_soup(50000, seed=9, extent=0.03)
+    scene = Scene(prim, 0)
+    os.environ["TRQ_CHUNK_RAYS"] = "16384"
+    try:
+        for n in (16384 * 6, 16384 * 6 + 1, 16384 * 9 + 777, 16384 * 5 + 3, 1000):
+            rays = H.random_rays(n, seed=n % 97)
+            dev = scene.hit(rays_to_torch(rays, "cuda:0")).cpu().numpy().view(L.hit_dtype).reshape(-1)
+            for h16 in (False, True):
+                host = scene.hit(rays, hit16=h16)
+                want = L.pack_hit16(dev) if h16 else dev
+                assert np.array_equal(host.view(np.uint8), want.view(np.uint8)), (n, h16)
+    finally:
+        del os.environ["TRQ_CHUNK_RAYS"]
+    scene.close()

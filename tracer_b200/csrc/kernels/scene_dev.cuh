@@ -13,7 +13,18 @@
 //       t0 = { v0.xyz, bits(leafNode) }  t1 = { v1 - v0, 0 }  t2 = { v2 - v0, 0 }  (t3 unused)
 //     (the two edge subtractions are the first operations of Triangle::hit_test, Triangle.hh:43-44)
 //   packed spheres 32 B = 2 x float4 per sphere LEAF:
-//       s0 = { center.xyz, radius }      s1 = { bits(leafNode), 0, 0, 0 }
+//       s0 = { center.xyz, radius }      s1 = { bits(leafNode), bits(pIndex), bits(material), 0 }
+//   packed squares 64 B = 4 x float4 per square LEAF (48 B used):
+//       q0 = { range_i.x, range_i.y, range_j.x, range_j.y }
+//       q1 = { value_k, bits(axis_i | axis_j << 8 | axis_k << 16), bits(material), bits(leafNode) }
+//       q2 = { bits(pIndex), 0, 0, 0 }
+//   triangle finish records 64 B per triangle LEAF (same slot as the packed triangle), read once per ray that ends on it:
+//       n0 = { normal0.xyz, bits(leafNode) }  n1 = { normal1.xyz, bits(pIndex) }  n2 = { normal2.xyz, 0 }
+//   Cube leaves are read in place from the 240-byte reference struct (two per Cornell box).
+//
+// Interior nodes are numbered so that the first `topNodes` of them are the top of the tree in breadth-first order (any
+// prefix of that block can be staged in shared memory by the kernel: "index < topCount" is the residency test); the rest
+// follow in depth-first order.
 //
 // Child reference (32 bit): kind in bits 31..29, index in bits 28..0.
 #pragma once
@@ -28,7 +39,7 @@ enum : uint32_t {
     REF_INTERIOR = 0u,   // index = packed interior node
     REF_TRI      = 1u,   // index = packed triangle slot
     REF_SPHERE   = 2u,   // index = packed sphere slot
-    REF_SQUARE   = 3u,   // index = leaf node in bvhList (reads the reference-layout Square)
+    REF_SQUARE   = 3u,   // index = packed square slot
     REF_CUBE     = 4u,   // index = leaf node in bvhList (reads the reference-layout Cube)
     REF_NOP      = 6u,   // leaf whose pType dispatches to `default: break` (Render.hh:241)
     REF_DONE     = 7u    // traversal finished (never stored in a node)
@@ -48,6 +59,7 @@ struct SceneDev {
     const float4*    nodes;     // 4 per interior node
     const float4*    tris;      // 3 per triangle leaf
     const float4*    sph;       // 2 per sphere leaf
+    const float4*    sq;        // 4 per square leaf
     const float4*    triN;      // 4 per triangle leaf (same slot as tris): {n0, leafNode} {n1, pIndex} {n2, 0} {pad}
     uint32_t         rootRef;
     float            rootMin[3], rootMax[3];
@@ -65,18 +77,15 @@ struct CompactHit {
     float    dy, dz;     // ray direction y, z (triangle front-face test in resolve_hits without re-reading the ray)
 };
 
-// Peer-memory hit gather (trq_trace_gather): where the resolve kernel also writes every trq_hit, over NVLink, and
-// how it tells the peers that this rank's slot is complete.
-#define TRQ_GATHER_MAX_RANKS 16
-struct GatherDev {
-    trq_hit*            peerSlot[TRQ_GATHER_MAX_RANKS];    // slot [rank] of this step's buffer on every OTHER rank
-    unsigned long long* peerFlag[TRQ_GATHER_MAX_RANKS];    // flags[rank] on every other rank: last completed step
-    unsigned long long* peerCount[TRQ_GATHER_MAX_RANKS];   // counts[parity][rank] on every other rank
-    unsigned long long* ownFlag;                           // the same two words in this rank's own header
-    unsigned long long* ownCount;
-    uint32_t            nPeer;
-    unsigned int*       blocksDone;                        // local: CTAs of the resolve kernel that have finished
-    unsigned long long  step;
+// Work-queue head of one trace launch: `head` is the next unclaimed queue slot; `done` counts CTAs that have left the
+// kernel. The last CTA to leave zeroes both, so a head is always zero between launches (no memset, no resolve pass).
+struct QueueHead {
+    unsigned long long head;
+    unsigned int       done;
+    unsigned int       pad;
 };
+
+#define TRQ_GATHER_MAX_RANKS 16
+#define TRQ_MAX_PEERS (TRQ_GATHER_MAX_RANKS - 1)
 
 }  // namespace trq

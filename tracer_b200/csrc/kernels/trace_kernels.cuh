@@ -2,20 +2,23 @@
 //
 //   trace_reflayout_kernel  1:1 transcription of Scene::hit (Render.hh:135-252) over the reference-
 //                           layout buffers: parent links + 32-bit trail, one thread per ray.
-//                           Correctness anchor and naive baseline.
+//                           Correctness anchor and naive baseline (followed by resolve_hits_kernel).
 //   trace_packed_kernel     the product kernel: persistent warps pull rays from a global queue with
 //                           one warp-aggregated atomic per refill, traverse the packed 64-B fused
-//                           nodes with 256-bit loads, and keep the far children of "both hit" nodes
+//                           nodes with 256-bit loads (the top levels optionally from a TMA-staged copy in
+//                           shared memory), and keep the far children of "both hit" nodes
 //                           on a per-lane shared-memory stack. The stack replaces the reference's
 //                           from-child steps (re-reading parent links, Render.hh:189-209); the visit
 //                           ORDER per ray is exactly the reference's: near child first by hit_t's t,
 //                           ties to the right child, the far child decided at first arrival and never
 //                           re-tested, including the "select the missed child" quirk of Render.hh:174.
-//                           FUSED variant (triangle-only scenes): writes the final trq_hit when a ray retires.
-//   resolve_hits_kernel     compact result -> trq_hit (pType, pIndex, front, material, sphere uv) for scenes with
-//                           sphere / square / cube leaves; GATHER variant also stores the record to every peer GPU
+//                           A retiring ray's FINAL record (trq_hit, or the 16-byte trq_hit16) is written by
+//                           this kernel for every leaf type -- there is no second pass over the batch -- and,
+//                           when a gather is attached, stored into every peer GPU's buffer from the same
+//                           place (compute + all-gather in one kernel, over NVLink peer memory).
 //   sort_*_kernel           optional ordering of the work queue (TRQ_SORT_RAYS)
 //   expand_hits_kernel      trq_hit -> HitRecord fields (p, gn, sn, uv, f, material)
+//   pack_scene_kernel       reference-layout arrays -> packed traversal layout, on the device
 #pragma once
 #include <cfloat>
 
@@ -154,26 +157,6 @@ trace_reflayout_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// v1: packed layout, persistent warps, shared-memory far-child stack.
-#ifndef TRQ_BLOCK
-#define TRQ_BLOCK 256
-#endif
-
-#define TRQ_TRI_STRIDE 4u      // float4 per packed triangle: 64-byte records (48 used) so that a test is two requests, never three
-
-struct TraceParams {
-    const trq_ray* rays;
-    trq_hit*       hits;
-    uint64_t       n;
-    unsigned long long* counter;   // global ray queue head
-    uint32_t       stackDepth;     // entries per lane
-    uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
-    uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
-    const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
-    const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
-};
-
-// ---------------------------------------------------------------------------------------------
 // Optional ray ordering (TRQ_SORT_RAYS): a counting sort of ray INDICES by (Morton cell of the origin inside the
 // scene box, direction octant), so that the rays one warp pulls from the queue start in the same region and head
 // the same way. Rays are not moved; hits are still written at the ray's own index; the per-ray traversal is
@@ -261,31 +244,185 @@ sort_scatter_kernel(const uint32_t* __restrict__ keys, uint64_t n, const unsigne
     order[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;     // lanes keep their index order inside a group
 }
 
-// Per-ray state that the interior loop never touches is parked in shared memory ([word][TRQ_BLOCK],
-// lane-major => bank-conflict free) so that the hot loop fits in 48 registers (5 resident CTAs per SM).
+// ---------------------------------------------------------------------------------------------
+// v1: packed layout, persistent warps, shared-memory far-child stack, records finished in the kernel.
+#define TRQ_TRI_STRIDE 4u      // float4 per packed triangle: 64-byte records (48 used) so that a test is two requests, never three
+#define TRQ_SQ_STRIDE  4u      // float4 per packed square
+
+// Output record formats of the packed kernel
+enum : int { OUT_HIT32 = 0, OUT_HIT16 = 1 };
+
+struct TraceParams {
+    const trq_ray* rays;
+    void*          hits;           // trq_hit[n] (OUT_HIT32) or trq_hit16[n] (OUT_HIT16)
+    uint64_t       n;
+    QueueHead*     queue;          // global ray queue head of this launch (zero on entry, zeroed again by the last CTA)
+    uint32_t       stackDepth;     // entries per lane
+    uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
+    uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
+    uint32_t       topCount;       // interior nodes [0, topCount) are staged in shared memory (TOP kernels), else 0
+    const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
+    const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
+    // Peer fan-out (trq_trace_gather): every finished record is also stored at the same index of nPeer remote buffers
+    // (NVLink peer memory); the last CTA to leave publishes (count, step) to this rank's and every peer's header.
+    uint32_t            nPeer;
+    uint32_t            pad;
+    unsigned long long  step;
+    unsigned long long* ownFlag;
+    unsigned long long* ownCount;
+    void*               peerHits[TRQ_MAX_PEERS];
+    unsigned long long* peerFlag[TRQ_MAX_PEERS];
+    unsigned long long* peerCount[TRQ_MAX_PEERS];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg4(void* p, const float4& a) {
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+}
+
+// trq_hit (two float4) -> trq_hit16 {t, id, u, v}; id = 0xffffffff on a miss, else front << 31 | pType << 28 | pIndex
+__device__ __forceinline__ float4 pack_hit16(const float4& o0, const float4& o1) {
+    const uint32_t flags = __float_as_uint(o1.w);
+    const uint32_t id = (flags & TRQ_HIT_FLAG_HIT)
+        ? (((flags & TRQ_HIT_FLAG_FRONT) ? 0x80000000u : 0u) | (__float_as_uint(o0.y) << 28) | (__float_as_uint(o0.z) & 0x0fffffffu))
+        : 0xffffffffu;
+    return make_float4(o0.x, __uint_as_float(id), o1.x, o1.y);
+}
+
+// One finished record to this rank's buffer and to the same index of every peer's.
+template <int OUT>
+__device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, const float4& o0, const float4& o1) {
+    if (OUT == OUT_HIT32) {
+        stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
+#pragma unroll 1
+        for (uint32_t p = 0; p < P.nPeer; ++p) stg8(reinterpret_cast<trq_hit*>(P.peerHits[p]) + idx, o0, o1);
+    } else {
+        const float4 c = pack_hit16(o0, o1);
+        stg4(reinterpret_cast<float4*>(P.hits) + idx, c);
+#pragma unroll 1
+        for (uint32_t p = 0; p < P.nPeer; ++p) stg4(reinterpret_cast<float4*>(P.peerHits[p]) + idx, c);
+    }
+}
+
+// Cube::hit_test on the 240-byte reference struct (two per Cornell box: rare). Out of line and fed with scalars by
+// value so that the hot loops keep the ray in registers. out = {t, u, v, bits(front | material << 1)}.
+// (TAG: one copy per kernel instantiation -- ptxas 12.9 crashes when two entries with different launch bounds share
+// an out-of-line function.)
+template <int TAG>
+__device__ __noinline__ bool leaf_cube(const RefBVH* __restrict__ bvh, const RefCube* __restrict__ cubes, uint32_t leafNode,
+                                       float ox, float oy, float oz, float dx, float dy, float dz, float range_y, float4* out) {
+    const RayCtx ray = make_ray_ctx(ox, oy, oz, dx, dy, dz);
+    float t = 0.0f;
+    Surface s;
+    if (!cube_hit(&cubes[bvh[leafNode].pIndex], ray, FLT_MIN, range_y, t, &s)) return false;
+    *out = make_float4(t, s.uvx, s.uvy, __uint_as_float(s.front | (s.material << 1)));
+    return true;
+}
+
+// The final trq_hit of a ray that ended on a sphere / square / cube leaf (the triangle case is inline in flush()).
+//   sphere: Sphere.hh:51-56 (p, gn = (p - c) / r, checkFace, sphereUV)      square: Square.hh:93-111 (uv, checkFace)
+//   cube:   front / material / uv were captured by leaf_cube at hit time
+template <int TAG>
+__device__ __noinline__ void finish_other(const float4* __restrict__ sph, const float4* __restrict__ sq, const RefBVH* __restrict__ bvh,
+                                          uint32_t best, float ox, float oy, float oz, float dx, float dy, float dz,
+                                          float t, float u, float v, uint32_t aux, float4* out) {
+    const uint32_t kind = TRQ_REF_KIND(best), slot = TRQ_REF_INDEX(best);
+    const f3 o = make_f3(ox, oy, oz), d = make_f3(dx, dy, dz);
+    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+    if (kind == REF_SPHERE) {
+        const float4 s0 = ldg4(sph + (size_t)slot * 2u), s1 = ldg4(sph + (size_t)slot * 2u + 1);
+        const f3 p = add3(o, scale3(d, t));
+        const f3 gn = divs3(sub3(p, make_f3(s0.x, s0.y, s0.z)), s0.w);
+        const uint32_t front = front_face(d, gn) ? TRQ_HIT_FLAG_FRONT : 0u;
+        const float phi = atan2f(gn.z, gn.x);
+        const float theta = asinf(gn.y);
+        const float uvx = fsub(1.0f, fdiv(fadd(phi, TRQ_PI_F), fmul(2.0f, TRQ_PI_F)));
+        const float uvy = fdiv(fadd(theta, TRQ_PI_2_F), TRQ_PI_F);
+        o0 = make_float4(t, __uint_as_float((uint32_t)TRQ_SPHERE), s1.y, s1.x);
+        o1 = make_float4(uvx, uvy, s1.z, __uint_as_float(TRQ_HIT_FLAG_HIT | front));
+    } else if (kind == REF_SQUARE) {
+        const float4* qp = sq + (size_t)slot * TRQ_SQ_STRIDE;
+        float4 q0, q1;
+        ldg8(qp, q0, q1);
+        const float4 q2 = ldg4(qp + 2);
+        const uint32_t axes = __float_as_uint(q1.y);
+        const unsigned ai = axes & 3u, aj = (axes >> 8) & 3u, ak = (axes >> 16) & 3u;
+        const float a = fadd(get3(o, ai), fmul(t, get3(d, ai)));                   // Square.hh:88,91 with the accepted t
+        const float b = fadd(get3(o, aj), fmul(t, get3(d, aj)));
+        const float uvx = fdiv(fsub(a, q0.x), fsub(q0.y, q0.x));                   // :96-97
+        const float uvy = fdiv(fsub(b, q0.z), fsub(q0.w, q0.z));
+        f3 gn = make_f3(0.0f, 0.0f, 0.0f);
+        set3(gn, ak, 1.0f);
+        const uint32_t front = front_face(d, gn) ? TRQ_HIT_FLAG_FRONT : 0u;       // :99-100
+        o0 = make_float4(t, __uint_as_float((uint32_t)TRQ_SQUARE), q2.x, q1.w);
+        o1 = make_float4(uvx, uvy, q1.z, __uint_as_float(TRQ_HIT_FLAG_HIT | front));
+    } else if (kind == REF_CUBE) {
+        o0 = make_float4(t, __uint_as_float((uint32_t)TRQ_CUBE), __uint_as_float(bvh[slot].pIndex), __uint_as_float(slot));
+        o1 = make_float4(u, v, __uint_as_float(aux >> 1), __uint_as_float(TRQ_HIT_FLAG_HIT | ((aux & 1u) ? TRQ_HIT_FLAG_FRONT : 0u)));
+    }
+    out[0] = o0; out[1] = o1;
+}
+
+// Per-ray state that the interior loop never touches is parked in shared memory ([word][BLOCK],
+// lane-major => bank-conflict free) so that the hot loop fits in 48 registers (5 resident CTAs of 256 per SM).
 enum : uint32_t { COLD_TEST_T = 0, COLD_BEST, COLD_U, COLD_V, COLD_AUX, COLD_RAY, COLD_DX, COLD_DY, COLD_DZ, COLD_WORDS };
 
 #ifndef TRQ_INTERIOR_UNROLL
 #define TRQ_INTERIOR_UNROLL 2
 #endif
-#ifndef TRQ_MIN_BLOCKS
-#define TRQ_MIN_BLOCKS 5
+#ifndef TRQ_WAIT_MUL
+#define TRQ_WAIT_MUL 2
 #endif
 
 #ifdef TRQ_STATS
 __device__ unsigned long long g_stats[8];
 #endif
 
-// FUSED (triangle-only scenes): a retiring ray's final trq_hit is written by this kernel; otherwise a compact result is
-// written and resolve_hits_kernel finishes it.
-template <bool ANY, bool FUSED>
-__global__ void __launch_bounds__(TRQ_BLOCK, TRQ_MIN_BLOCKS)
+// Top-of-tree staging (TOP kernels): one TMA bulk copy (cp.async.bulk, completion on an mbarrier) brings the first
+// topCount packed nodes -- the top levels of the tree in breadth-first order -- into shared memory when the CTA starts.
+__device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src, uint32_t bytes, unsigned long long* mbar) {
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (bytes == 0) return;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+    }
+    uint32_t ready = 0;
+    while (!ready) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ready) : "r"(mb) : "memory");
+    }
+}
+
+// ANY: Scene::hit(any = true). OUT: record format. BLOCK x MINB: CTA size and resident CTAs per SM.
+// TOP: the first P.topCount interior nodes are read from shared memory instead of L1/L2.
+template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP>
+__global__ void __launch_bounds__(BLOCK, MINB)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
-    extern __shared__ uint32_t smem_u32[];
-    uint32_t* const stk = smem_u32 + threadIdx.x;                                   // [stackDepth][TRQ_BLOCK]
-    uint32_t* const cold = smem_u32 + P.stackDepth * TRQ_BLOCK + threadIdx.x;        // [COLD_WORDS][TRQ_BLOCK]
+    extern __shared__ __align__(128) uint32_t smem_u32[];
+    __shared__ unsigned long long topBarrier;
+    const uint32_t topWords = TOP ? P.topCount * 16u : 0u;
+    const float4* const topNodes = reinterpret_cast<const float4*>(smem_u32);        // [topCount][4]
+    uint32_t* const stk = smem_u32 + topWords + threadIdx.x;                         // [stackDepth][BLOCK]
+    uint32_t* const cold = smem_u32 + topWords + P.stackDepth * BLOCK + threadIdx.x; // [COLD_WORDS][BLOCK]
     float* const coldf = reinterpret_cast<float*>(cold);
     const unsigned lane = threadIdx.x & 31u;
+    constexpr int TAG = ((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT;
+
+    if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.nodes, P.topCount * 64u, &topBarrier);
 
     const uint64_t N = live_count(P.n, P.nPtr);
     bool active = false, exhausted = false;
@@ -293,46 +430,44 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     float range_y = 0.0f;
     uint32_t cur = TRQ_REF_DONE_WORD, sp = 0;
 
-    // A finished ray only retires its lane; its compact result (resolved into trq_hit by resolve_hits_kernel) is
-    // written by flush() when the warp next refills, for all retired lanes at once: the six shared-memory reads and the
-    // store are then issued once per refill instead of once per finishing ray (most rays finish alone in their warp step).
+    // A finished ray only retires its lane; its record is finished and written by flush() when the warp next refills,
+    // for all retired lanes at once: the shared-memory reads, the finish-record fetch and the store(s) are then issued
+    // once per refill instead of once per finishing ray (most rays finish alone in their warp step). The lane's
+    // registers (ro, range_y) stay untouched between finish() and flush().
     bool pending = false;
     auto finish = [&]() { active = false; pending = true; };
     auto flush = [&]() {
         if (pending) {
-            const uint32_t best = cold[COLD_BEST * TRQ_BLOCK];
-            const bool hit = (range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) && best != 0xffffffffu;   // Render.hh:251
-            if (FUSED) {
-                // triangle-only scene: `best` is the triangle slot; finish the record here (Triangle.hh:73-82: interpolated
-                // normal, checkFace) and write the final trq_hit -- no resolve pass over the batch afterwards
-                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-                if (hit) {
-                    const float4* np = S.triN + (size_t)best * 4u;
+            const uint32_t best = cold[COLD_BEST * BLOCK];
+            const bool hit = (range_y < coldf[COLD_TEST_T * BLOCK]) && best != 0xffffffffu;   // Render.hh:251
+            float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+            if (hit) {
+                const float u = coldf[COLD_U * BLOCK], v = coldf[COLD_V * BLOCK];
+                const f3 d = make_f3(coldf[COLD_DX * BLOCK], coldf[COLD_DY * BLOCK], coldf[COLD_DZ * BLOCK]);
+                if (TRQ_REF_KIND(best) == REF_TRI) {
+                    // Triangle.hh:73-82: interpolated normal, checkFace; ids from the finish record
+                    const float4* np = S.triN + (size_t)TRQ_REF_INDEX(best) * 4u;
                     float4 q0, q1;
                     ldg8(np, q0, q1);
                     const float4 q2 = ldg4(np + 2);
-                    const float u = coldf[COLD_U * TRQ_BLOCK], v = coldf[COLD_V * TRQ_BLOCK];
                     const float w = fsub(fsub(1.0f, u), v);
                     const f3 gn = add3(add3(scale3(make_f3(q1.x, q1.y, q1.z), u), scale3(make_f3(q2.x, q2.y, q2.z), v)),
                                        scale3(make_f3(q0.x, q0.y, q0.z), w));
-                    const f3 d = make_f3(__uint_as_float(cold[COLD_AUX * TRQ_BLOCK]), coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
                     const uint32_t front = front_face(d, gn) ? TRQ_HIT_FLAG_FRONT : 0u;
                     o0 = make_float4(range_y, __uint_as_float((uint32_t)TRQ_TRIANGLE), q1.w, q0.w);
                     o1 = make_float4(u, v, __uint_as_float(19u), __uint_as_float(TRQ_HIT_FLAG_HIT | front));
+                } else {
+                    float4 o[2];
+                    finish_other<TAG>(S.sph, S.sq, S.bvh, best, ro.x, ro.y, ro.z, d.x, d.y, d.z, range_y, u, v, cold[COLD_AUX * BLOCK], o);
+                    o0 = o[0]; o1 = o[1];
                 }
-                stg8(P.hits + cold[COLD_RAY * TRQ_BLOCK], o0, o1);
-            } else {
-                // triangle / sphere hits carry the ray direction (aux word = d.x) so that resolve_hits_kernel does not
-                // have to read the ray again for the front-face test
-                store_compact(P.hits, cold[COLD_RAY * TRQ_BLOCK], hit, range_y, best,
-                              coldf[COLD_U * TRQ_BLOCK], coldf[COLD_V * TRQ_BLOCK], cold[COLD_AUX * TRQ_BLOCK],
-                              coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
             }
+            emit_record<OUT>(P, cold[COLD_RAY * BLOCK], o0, o1);
             pending = false;
         }
     };
     auto pop = [&]() {
-        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * TRQ_BLOCK]; }
+        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * BLOCK]; }
     };
 
     for (;;) {
@@ -344,7 +479,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             if (lane == 0) { atomicAdd(&g_stats[4], 1ull); atomicAdd(&g_stats[5], (unsigned long long)want); }
 #endif
             unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)want);
+            if (lane == 0) base = atomicAdd(&P.queue->head, (unsigned long long)want);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base + (unsigned long long)want >= N) exhausted = true;
             flush();
@@ -361,15 +496,16 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
                     const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
                     if (box_hit(rootMin, rootMax, ray, FLT_MIN, range_y)) {            // :145
-                        coldf[COLD_TEST_T * TRQ_BLOCK] = r0.w;
-                        cold[COLD_BEST * TRQ_BLOCK] = 0xffffffffu;
-                        coldf[COLD_U * TRQ_BLOCK] = 0.0f; coldf[COLD_V * TRQ_BLOCK] = 0.0f;
-                        cold[COLD_AUX * TRQ_BLOCK] = 0u;
-                        cold[COLD_RAY * TRQ_BLOCK] = (uint32_t)idx;
-                        coldf[COLD_DX * TRQ_BLOCK] = r1.x; coldf[COLD_DY * TRQ_BLOCK] = r1.y; coldf[COLD_DZ * TRQ_BLOCK] = r1.z;
+                        coldf[COLD_TEST_T * BLOCK] = r0.w;
+                        cold[COLD_BEST * BLOCK] = 0xffffffffu;
+                        coldf[COLD_U * BLOCK] = 0.0f; coldf[COLD_V * BLOCK] = 0.0f;
+                        cold[COLD_AUX * BLOCK] = 0u;
+                        cold[COLD_RAY * BLOCK] = (uint32_t)idx;
+                        coldf[COLD_DX * BLOCK] = r1.x; coldf[COLD_DY * BLOCK] = r1.y; coldf[COLD_DZ * BLOCK] = r1.z;
                         cur = S.rootRef; active = true;
                     } else {
-                        store_compact(P.hits, idx, false, 0.0f, 0u, 0.0f, 0.0f, 0u);
+                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        emit_record<OUT>(P, (uint32_t)idx, z, z);
                     }
                 }
             }
@@ -392,21 +528,26 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 // leave the interior phase once the lanes waiting at a leaf are more than half of those still stepping
                 // (B200 sweep, C3 / 1 M soup Mrays/s: never 4094 / 1141, nWait > nInt 4650 / 1154, 2 nWait > nInt 4727 / 1158,
                 // 3x 4701 / 1157, 4x 4678 / 1158, 6x 4614 / 1155)
-#ifndef TRQ_WAIT_MUL
-#define TRQ_WAIT_MUL 2
-#endif
                 if (nInt == 0 || nWait >= (int)P.leafBatch || TRQ_WAIT_MUL * nWait > nInt) break;
 #pragma unroll
                 for (int rep = 0; rep < TRQ_INTERIOR_UNROLL; ++rep) {          // steps per vote round
 #ifdef TRQ_STATS
                     { const unsigned m_ = __ballot_sync(0xffffffffu, active && TRQ_REF_KIND(cur) == REF_INTERIOR);
-                      if (lane == 0 && m_) { atomicAdd(&g_stats[0], 1ull); atomicAdd(&g_stats[1], (unsigned long long)__popc(m_)); } }
+                      if (lane == 0 && m_) { atomicAdd(&g_stats[0], 1ull); atomicAdd(&g_stats[1], (unsigned long long)__popc(m_)); }
+                      const unsigned t_ = __ballot_sync(0xffffffffu, active && TRQ_REF_KIND(cur) == REF_INTERIOR && TOP && TRQ_REF_INDEX(cur) < P.topCount);
+                      if (lane == 0 && t_) atomicAdd(&g_stats[6], (unsigned long long)__popc(t_)); }
 #endif
                     if (active && TRQ_REF_KIND(cur) == REF_INTERIOR) {
-                        const float4* np = S.nodes + (size_t)TRQ_REF_INDEX(cur) * 4u;
+                        const uint32_t ni = TRQ_REF_INDEX(cur);
                         float4 q0, q1, q2, q3;
-                        ldg8(np, q0, q1);
-                        ldg8(np + 2, q2, q3);
+                        if (TOP && ni < P.topCount) {                         // top of the tree: four LDS.128 from this CTA's copy
+                            const float4* tp = topNodes + ni * 4u;
+                            q0 = tp[0]; q1 = tp[1]; q2 = tp[2]; q3 = tp[3];
+                        } else {
+                            const float4* np = S.nodes + (size_t)ni * 4u;
+                            ldg8(np, q0, q1);
+                            ldg8(np + 2, q2, q3);
+                        }
                         float tl = range_y, tr = range_y;                     // :157
                         const bool lt = box_entry(make_f3(q0.x, q0.y, q0.z), make_f3(q1.x, q1.y, q1.z), ro, rinv, range_y, tl);   // :159
                         const bool rt = box_entry(make_f3(q2.x, q2.y, q2.z), make_f3(q3.x, q3.y, q3.z), ro, rinv, range_y, tr);   // :160
@@ -415,7 +556,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                             pop();
                         } else {
                             const bool selLeft = tl < tr;                     // :174 (ties -> right, quirk included)
-                            if (lt && rt) { stk[sp * TRQ_BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
+                            if (lt && rt) { stk[sp * BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
                             cur = selLeft ? lref : rref;
                         }
                         if (cur == TRQ_REF_DONE_WORD) finish();
@@ -430,125 +571,129 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 const uint32_t kind = TRQ_REF_KIND(cur);
                 RayCtx ray;
                 ray.o = ro; ray.inv = rinv;
-                ray.d = make_f3(coldf[COLD_DX * TRQ_BLOCK], coldf[COLD_DY * TRQ_BLOCK], coldf[COLD_DZ * TRQ_BLOCK]);
-                bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t leaf = 0, a = 0;
+                ray.d = make_f3(coldf[COLD_DX * BLOCK], coldf[COLD_DY * BLOCK], coldf[COLD_DZ * BLOCK]);
+                bool h = false; float t = 0.0f, u = 0.0f, v = 0.0f; uint32_t a = 0;
                 if (kind == REF_TRI) {
                     const float4* tp = S.tris + (size_t)TRQ_REF_INDEX(cur) * TRQ_TRI_STRIDE;
                     float4 t0, t1;
                     ldg8(tp, t0, t1);                                       // one 256-bit + one 128-bit request per test
                     const float4 t2 = ldg4(tp + 2);
-                    leaf = __float_as_uint(t0.w);
                     h = tri_hit(make_f3(t0.x, t0.y, t0.z), make_f3(t1.x, t1.y, t1.z), make_f3(t2.x, t2.y, t2.z),
                                 ray, FLT_MIN, range_y, t, u, v);
                 } else if (kind == REF_SPHERE) {
-                    const float4* spp = S.sph + (size_t)TRQ_REF_INDEX(cur) * 2u;
-                    const float4 s0 = ldg4(spp), s1 = ldg4(spp + 1);
-                    leaf = __float_as_uint(s1.x);
+                    const float4 s0 = ldg4(S.sph + (size_t)TRQ_REF_INDEX(cur) * 2u);
                     h = sphere_hit(make_f3(s0.x, s0.y, s0.z), s0.w, ray, FLT_MIN, range_y, t);
-                } else if (kind == REF_SQUARE || kind == REF_CUBE) {
-                    leaf = TRQ_REF_INDEX(cur);
+                } else if (kind == REF_SQUARE) {
+                    // Square::hit_test (Square.hh:82-92) on the packed record; the rejections are pure comparisons, and-ed
+                    float4 q0, q1;
+                    ldg8(S.sq + (size_t)TRQ_REF_INDEX(cur) * TRQ_SQ_STRIDE, q0, q1);
+                    const uint32_t axes = __float_as_uint(q1.y);
+                    const unsigned ai = axes & 3u, aj = (axes >> 8) & 3u, ak = (axes >> 16) & 3u;
+                    const float tt = fdiv(fsub(q1.x, get3(ro, ak)), get3(ray.d, ak));
+                    bool ok = !(isinf(tt) || isnan(tt)) && !(tt < FLT_MIN || tt > range_y);
+                    const float sa = fadd(get3(ro, ai), fmul(tt, get3(ray.d, ai)));
+                    ok = ok && !(sa < q0.x || sa > q0.y);
+                    const float sb = fadd(get3(ro, aj), fmul(tt, get3(ray.d, aj)));
+                    ok = ok && !(sb < q0.z || sb > q0.w);
+                    if (ok) { h = true; t = tt; }
+                } else if (kind == REF_CUBE) {
                     float4 o4;
-                    h = leaf_square_cube(S.bvh, S.squares, S.cubes, kind, leaf, ro.x, ro.y, ro.z, ray.d.x, ray.d.y, ray.d.z, range_y, &o4);
+                    h = leaf_cube<TAG>(S.bvh, S.cubes, TRQ_REF_INDEX(cur), ro.x, ro.y, ro.z, ray.d.x, ray.d.y, ray.d.z, range_y, &o4);
                     if (h) { t = o4.x; u = o4.y; v = o4.z; a = __float_as_uint(o4.w); }
                 }
                 if (h) {
                     range_y = t;
-                    cold[COLD_BEST * TRQ_BLOCK] = FUSED ? TRQ_REF_INDEX(cur) : leaf;
-                    coldf[COLD_U * TRQ_BLOCK] = u; coldf[COLD_V * TRQ_BLOCK] = v;
-                    cold[COLD_AUX * TRQ_BLOCK] = (kind == REF_SQUARE || kind == REF_CUBE) ? a : __float_as_uint(ray.d.x);
+                    cold[COLD_BEST * BLOCK] = cur;
+                    coldf[COLD_U * BLOCK] = u; coldf[COLD_V * BLOCK] = v;
+                    cold[COLD_AUX * BLOCK] = a;
                 }
-                if (ANY && range_y < coldf[COLD_TEST_T * TRQ_BLOCK]) cur = TRQ_REF_DONE_WORD;   // :244
+                if (ANY && range_y < coldf[COLD_TEST_T * BLOCK]) cur = TRQ_REF_DONE_WORD;   // :244
                 else pop();
                 if (cur == TRQ_REF_DONE_WORD) finish();
             }
         } while (__popc(__ballot_sync(0xffffffffu, active)) > keepGoing);
     }
-}
 
-// ---------------------------------------------------------------------------------------------
-// compact -> trq_hit, in place. One thread per ray, fully coalesced.
-// GATHER: the resolved record is also stored into this rank's slot of every peer's buffer (NVLink peer memory, one
-// coalesced 1-KB run per warp and peer); the last CTA to finish publishes count and step number to every peer with
-// system-scope release stores, which the peers' gather_wait_kernel acquires.
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <bool GATHER>
-__global__ void __launch_bounds__(256)
-resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n, const unsigned long long* __restrict__ nPtr,
-                    unsigned long long* queueHead, const GatherDev G) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0 && queueHead) *queueHead = 0ull;        // the trace that used this queue head finished before this kernel started
-    const uint64_t live = live_count(n, nPtr);
-    if (i < live) {
-        float4* io = reinterpret_cast<float4*>(hits + i);
-        const float4 a = io[0], b = io[1];
-        trq_hit out;
-        out.t = 0.0f; out.pType = 0; out.pIndex = 0; out.leafNode = 0; out.u = 0.0f; out.v = 0.0f; out.material = 0; out.flags = 0;
-        if (__float_as_uint(b.y) != 0u) {
-            const uint32_t leaf = __float_as_uint(a.y);
-            const int32_t pType = S.bvh[leaf].pType;
-            const uint32_t pIndex = S.bvh[leaf].pIndex;
-            RayCtx ray;
-            if (pType == TRQ_TRIANGLE) {                          // only the direction matters (checkFace), and the trace kernel left it here
-                ray = make_ray_ctx(0.0f, 0.0f, 0.0f, b.x, b.z, b.w);
-            } else {
-                const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
-                const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
-                ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
-            }
-            out.t = a.x; out.pType = (uint32_t)pType; out.pIndex = pIndex; out.leafNode = leaf;
-            Surface s; s.front = 0; s.material = 0; s.uvx = s.uvy = 0.0f;
-            if (pType == TRQ_TRIANGLE) {
-                tri_surface(S.verts, S.idx, pIndex, a.z, a.w, ray, s);
-                out.u = a.z; out.v = a.w;
-            } else if (pType == TRQ_SPHERE) {
-                sphere_surface(&S.spheres[pIndex], a.x, ray, s);
-                out.u = s.uvx; out.v = s.uvy;
-            } else if (pType == TRQ_SQUARE) {
-                float t;
-                square_hit(&S.squares[pIndex], ray, a.x, a.x, t, &s);          // same t -> same a, b, uv
-                out.u = s.uvx; out.v = s.uvy;
-            } else if (pType == TRQ_CUBE) {
-                const uint32_t aux = __float_as_uint(b.x);
-                s.front = aux & 1u; s.material = aux >> 1;
-                out.u = a.z; out.v = a.w;
-            }
-            out.material = s.material;
-            out.flags = TRQ_HIT_FLAG_HIT | (s.front ? TRQ_HIT_FLAG_FRONT : 0u);
-        }
-        float4 o0, o1;
-        o0.x = out.t; o0.y = __uint_as_float(out.pType); o0.z = __uint_as_float(out.pIndex); o0.w = __uint_as_float(out.leafNode);
-        o1.x = out.u; o1.y = out.v; o1.z = __uint_as_float(out.material); o1.w = __uint_as_float(out.flags);
-        io[0] = o0; io[1] = o1;
-        if (GATHER) {
-#pragma unroll 1
-            for (uint32_t p = 0; p < G.nPeer; ++p) stg8(G.peerSlot[p] + i, o0, o1);
-        }
-    }
-    if (GATHER) {
-        __threadfence_system();                                   // this thread's peer stores before the CTA's arrival
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int prev = atomicAdd(G.blocksDone, 1u);
-            if (prev == gridDim.x - 1) {                          // last CTA: every record of this rank is on its way
-                *G.blocksDone = 0u;
+    // ---- epilogue: the last CTA to leave re-arms the queue head for the next launch that draws it and, when a gather
+    // is attached, publishes (count, step) to every rank -- after every thread's peer stores are fenced at system scope
+    if (P.ownFlag) __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(&P.queue->done, 1u);
+        if (prev == gridDim.x - 1) {
+            P.queue->head = 0ull;
+            P.queue->done = 0u;
+            if (P.ownFlag) {
                 __threadfence_system();
-                *G.ownCount = live;
-                st_release_sys(G.ownFlag, G.step);
-                for (uint32_t p = 0; p < G.nPeer; ++p) {
-                    *G.peerCount[p] = live;
-                    st_release_sys(G.peerFlag[p], G.step);
+                *P.ownCount = N;
+                st_release_sys(P.ownFlag, P.step);
+#pragma unroll 1
+                for (uint32_t p = 0; p < P.nPeer; ++p) {
+                    *P.peerCount[p] = N;
+                    st_release_sys(P.peerFlag[p], P.step);
                 }
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compact -> trq_hit, in place, for the reference-layout kernel (the packed kernel finishes its own records).
+// One thread per ray, fully coalesced.
+__global__ void __launch_bounds__(256)
+resolve_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, trq_hit* hits, uint64_t n, const unsigned long long* __restrict__ nPtr) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= live_count(n, nPtr)) return;
+    float4* io = reinterpret_cast<float4*>(hits + i);
+    const float4 a = io[0], b = io[1];
+    trq_hit out;
+    out.t = 0.0f; out.pType = 0; out.pIndex = 0; out.leafNode = 0; out.u = 0.0f; out.v = 0.0f; out.material = 0; out.flags = 0;
+    if (__float_as_uint(b.y) != 0u) {
+        const uint32_t leaf = __float_as_uint(a.y);
+        const int32_t pType = S.bvh[leaf].pType;
+        const uint32_t pIndex = S.bvh[leaf].pIndex;
+        RayCtx ray;
+        if (pType == TRQ_TRIANGLE) {                          // only the direction matters (checkFace), and the trace kernel left it here
+            ray = make_ray_ctx(0.0f, 0.0f, 0.0f, b.x, b.z, b.w);
+        } else {
+            const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
+            const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+            ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+        }
+        out.t = a.x; out.pType = (uint32_t)pType; out.pIndex = pIndex; out.leafNode = leaf;
+        Surface s; s.front = 0; s.material = 0; s.uvx = s.uvy = 0.0f;
+        if (pType == TRQ_TRIANGLE) {
+            tri_surface(S.verts, S.idx, pIndex, a.z, a.w, ray, s);
+            out.u = a.z; out.v = a.w;
+        } else if (pType == TRQ_SPHERE) {
+            sphere_surface(&S.spheres[pIndex], a.x, ray, s);
+            out.u = s.uvx; out.v = s.uvy;
+        } else if (pType == TRQ_SQUARE) {
+            float t;
+            square_hit(&S.squares[pIndex], ray, a.x, a.x, t, &s);          // same t -> same a, b, uv
+            out.u = s.uvx; out.v = s.uvy;
+        } else if (pType == TRQ_CUBE) {
+            const uint32_t aux = __float_as_uint(b.x);
+            s.front = aux & 1u; s.material = aux >> 1;
+            out.u = a.z; out.v = a.w;
+        }
+        out.material = s.material;
+        out.flags = TRQ_HIT_FLAG_HIT | (s.front ? TRQ_HIT_FLAG_FRONT : 0u);
+    }
+    float4 o0, o1;
+    o0.x = out.t; o0.y = __uint_as_float(out.pType); o0.z = __uint_as_float(out.pIndex); o0.w = __uint_as_float(out.leafNode);
+    o1.x = out.u; o1.y = out.v; o1.z = __uint_as_float(out.material); o1.w = __uint_as_float(out.flags);
+    io[0] = o0; io[1] = o1;
+}
+
+// trq_hit -> trq_hit16 (for the paths that do not produce it directly: the reference-layout kernel)
+__global__ void __launch_bounds__(256)
+pack_hit16_kernel(const trq_hit* __restrict__ hits, float4* __restrict__ out, uint64_t n, const unsigned long long* __restrict__ nPtr) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= live_count(n, nPtr)) return;
+    const float4* in = reinterpret_cast<const float4*>(hits + i);
+    out[i] = pack_hit16(in[0], in[1]);
 }
 
 // Waits (on the stream) until every rank has published `step`; gives up after timeoutNs and raises *status.
@@ -602,8 +747,9 @@ expand_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, const trq_hit* 
 __global__ void __launch_bounds__(256)
 pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ ref, uint32_t nNode,
                   const RefVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
-                  const RefSphere* __restrict__ spheres,
-                  float4* __restrict__ nodes, float4* __restrict__ tris, float4* __restrict__ sph, float4* __restrict__ triN) {
+                  const RefSphere* __restrict__ spheres, const RefSquare* __restrict__ squares,
+                  float4* __restrict__ nodes, float4* __restrict__ tris, float4* __restrict__ sph, float4* __restrict__ sq,
+                  float4* __restrict__ triN) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nNode) return;
     const uint32_t my = ref[i];
@@ -636,7 +782,15 @@ pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ r
         const RefSphere* s = &spheres[bvh[i].pIndex];
         float4* out = sph + (size_t)slot * 2u;
         out[0] = make_float4(s->center[0], s->center[1], s->center[2], s->radius);
-        out[1] = make_float4(__uint_as_float(i), 0.0f, 0.0f, 0.0f);
+        out[1] = make_float4(__uint_as_float(i), __uint_as_float(bvh[i].pIndex), __uint_as_float(s->material), 0.0f);
+    } else if (kind == REF_SQUARE) {
+        const RefSquare* q = &squares[bvh[i].pIndex];
+        float4* out = sq + (size_t)slot * TRQ_SQ_STRIDE;
+        const uint32_t axes = (uint32_t)q->axis_i | ((uint32_t)q->axis_j << 8) | ((uint32_t)q->axis_k << 16);
+        out[0] = make_float4(q->range_i[0], q->range_i[1], q->range_j[0], q->range_j[1]);
+        out[1] = make_float4(q->value_k, __uint_as_float(axes), __uint_as_float(q->material), __uint_as_float(i));
+        out[2] = make_float4(__uint_as_float(bvh[i].pIndex), 0.0f, 0.0f, 0.0f);
+        out[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 

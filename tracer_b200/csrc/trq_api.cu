@@ -50,9 +50,36 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-constexpr int kCounterRing = 256;
+constexpr int kQueueRing = 4096;           // queue heads handed out round-robin; each is zero between launches (the kernel
+                                           // re-arms it), so only > 4096 launches IN FLIGHT at once could alias one
 constexpr int kStageBufs = 4;
 constexpr int kProfRing = 64;
+constexpr uint32_t kTopMax = 2047;         // interior nodes numbered breadth-first at the front (11 full levels)
+constexpr size_t kSmemPerSM = 228u * 1024u, kSmemPerBlockMax = 227u * 1024u, kSmemBlockReserve = 1024u;
+
+// Launch configurations of trace_packed_kernel: CTA size x resident CTAs per SM, with or without the top of the tree
+// staged in shared memory. [any][record format] -> kernel.
+struct KernelCfg {
+    int block, minb;
+    bool top;
+    const void* fn[2][2];
+    const char* name;
+};
+#define TRQ_CFG(B, M, T)                                                                                      \
+    { B, M, T,                                                                                                \
+      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T> }, \
+        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T> } }, \
+      #B "x" #M #T }
+const KernelCfg kCfgs[] = {
+    TRQ_CFG(256, 5, false),       // 0: five CTAs of 256 threads per SM, every node from L1 / L2
+    TRQ_CFG(1024, 1, true),       // 1: one CTA of 1024 threads per SM sharing one staged copy of the top levels
+    TRQ_CFG(512, 2, true),        // 2: two CTAs of 512
+    TRQ_CFG(640, 2, true),        // 3: two CTAs of 640 (1280 threads per SM, as cfg 0)
+#ifdef TRQ_EXTRA_CFGS
+    TRQ_EXTRA_CFGS
+#endif
+};
+constexpr int kNumCfgs = (int)(sizeof(kCfgs) / sizeof(kCfgs[0]));
 #ifndef TRQ_DEFAULT_CHUNK_RAYS
 #define TRQ_DEFAULT_CHUNK_RAYS (512ll << 10)
 #endif
@@ -74,18 +101,21 @@ struct trq_scene {
     float4* d_nodes = nullptr;
     float4* d_tris = nullptr;
     float4* d_sph = nullptr;
+    float4* d_sq = nullptr;
     float4* d_triN = nullptr;
-    bool allTriangles = false;    // every leaf is a triangle: the trace kernel finishes its own records (no resolve pass)
     SceneDev dev{};
     uint32_t stackDepth = 1;
-    size_t traceSmem = 0;
-    int blocksPerSM[2][2] = {};   // resident trace_packed_kernel CTAs per SM: [closest-hit, any-hit][compact result, fused finish]
+    uint32_t maxPIndex = 0;       // largest leaf pIndex (trq_hit16 packs it into 28 bits)
+    // per launch configuration: staged top-of-tree nodes, dynamic shared memory, resident CTAs per SM [any][format]
+    struct CfgState { uint32_t topCount = 0; size_t smem = 0; int blocksPerSM[2][2] = {}; bool usable = false; };
+    CfgState cfg[kNumCfgs];
+    int defaultCfg = 0, autoCfg = 0;
     // stream-ordered scratch for TRQ_SORT_RAYS: a private pool that keeps its memory across synchronisations
     // (the device's default pool hands it back at every sync and re-maps 64 MB on the next sorted launch)
     cudaMemPool_t scratchPool = nullptr;
     // ray-queue heads
-    unsigned long long* d_counters = nullptr;
-    std::atomic<uint32_t> counterNext{0};
+    QueueHead* d_queues = nullptr;
+    std::atomic<uint32_t> queueNext{0};
     // staging for TRQ_HOST_PTRS
     std::mutex stageMutex;
     uint64_t stageCap = 0;
@@ -95,6 +125,7 @@ struct trq_scene {
     bool stageReady = false;
     uint64_t stageSeq = 0;        // chunks ever staged (ring position)
     // optional per-kernel timing (trq_profile_enable): events around the trace and resolve kernels
+    std::mutex profMutex;
     bool profile = false;
     cudaEvent_t evProf[kProfRing][3] = {};
     uint32_t profHead = 0, profCount = 0;
@@ -106,8 +137,8 @@ void free_scene(trq_scene* s) {
     if (!s) return;
     cudaFree(s->d_spheres); cudaFree(s->d_squares); cudaFree(s->d_cubes);
     cudaFree(s->d_verts); cudaFree(s->d_idx); cudaFree(s->d_bvh);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_triN);
-    cudaFree(s->d_counters);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_sq); cudaFree(s->d_triN);
+    cudaFree(s->d_queues);
     if (s->scratchPool) cudaMemPoolDestroy(s->scratchPool);
     for (int b = 0; b < kStageBufs; ++b) {
         cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
@@ -127,16 +158,21 @@ int upload(T** dst, const void* src, size_t count) {
     return TRQ_OK;
 }
 
-// Walk the tree once on the host: validate the layout contract and assign every reachable node its
-// packed reference (interior nodes and leaves numbered in depth-first order, left child first).
-int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_info_t& info) {
+// Walk the tree once on the host: validate the layout contract and assign every reachable node its packed reference.
+// Leaves are numbered per kind in depth-first order (left child first). Interior nodes: the first kTopMax of a
+// breadth-first walk come first, in that order (the block a kernel may stage in shared memory); the rest follow in
+// depth-first order.
+int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_info_t& info, uint32_t& maxPIndex) {
     const RefBVH* N = (const RefBVH*)d->bvhList;
     const uint32_t n = d->nNode;
     ref.assign(n, TRQ_REF_DONE_WORD);
-    uint32_t nInterior = 0, nTriLeaf = 0, nSphLeaf = 0, nLeaf = 0, maxDepth = 0;
+    uint32_t nTriLeaf = 0, nSphLeaf = 0, nSqLeaf = 0, nLeaf = 0, maxDepth = 0;
+    maxPIndex = 0;
+    std::vector<uint32_t> interiorDfs;                       // interior nodes in depth-first order
     struct Item { uint32_t node, depth; };
     std::vector<Item> stack;
     stack.push_back({0u, 0u});
+    if (N[0].parent != 0) return trq::fail(TRQ_ERR_LAYOUT, "bvhList: the root's parent must be 0 (BVH.hh:264), found %u", N[0].parent);
     while (!stack.empty()) {
         const Item it = stack.back(); stack.pop_back();
         const uint32_t i = it.node;
@@ -145,15 +181,23 @@ int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_i
         const RefBVH& b = N[i];
         if (b.pType == TRQ_BVH) {
             if (it.depth > 31) return trq::fail(TRQ_ERR_DEPTH, "bvhList: interior depth %u exceeds the 32-bit trail (Render.hh:140)", it.depth);
+            if (b.left >= n || b.right >= n)
+                return trq::fail(TRQ_ERR_LAYOUT, "bvhList: child index %u out of range (nNode %u)", b.left >= n ? b.left : b.right, n);
             if (b.left == 0 || b.right == 0 || b.left == b.right)
                 return trq::fail(TRQ_ERR_LAYOUT, "bvhList: interior node %u has invalid children (%u, %u)", i, b.left, b.right);
-            if (nInterior >= 0x1fffffffu) return trq::fail(TRQ_ERR_LAYOUT, "bvhList: too many interior nodes");
-            ref[i] = TRQ_MAKE_REF(REF_INTERIOR, nInterior++);
+            // Scene::hit climbs through `parent` (Render.hh:153,164,197): a child that does not point back would loop
+            if (N[b.left].parent != i || N[b.right].parent != i)
+                return trq::fail(TRQ_ERR_LAYOUT, "bvhList: children (%u, %u) of node %u do not name it as their parent (%u, %u)",
+                                 b.left, b.right, i, N[b.left].parent, N[b.right].parent);
+            if (interiorDfs.size() >= 0x1fffffffu) return trq::fail(TRQ_ERR_LAYOUT, "bvhList: too many interior nodes");
+            ref[i] = TRQ_MAKE_REF(REF_INTERIOR, 0);          // numbered below
+            interiorDfs.push_back(i);
             maxDepth = it.depth > maxDepth ? it.depth : maxDepth;
             stack.push_back({b.right, it.depth + 1});     // left is popped (numbered) first
             stack.push_back({b.left, it.depth + 1});
         } else {
             ++nLeaf;
+            if (b.pIndex > maxPIndex) maxPIndex = b.pIndex;
             switch (b.pType) {
                 case TRQ_TRIANGLE:
                     if (b.pIndex >= d->nTri) return trq::fail(TRQ_ERR_LAYOUT, "leaf %u: triangle pIndex %u >= nTri %u", i, b.pIndex, d->nTri);
@@ -168,7 +212,7 @@ int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_i
                     break;
                 case TRQ_SQUARE:
                     if (b.pIndex >= d->nSquare) return trq::fail(TRQ_ERR_LAYOUT, "leaf %u: square pIndex %u >= nSquare %u", i, b.pIndex, d->nSquare);
-                    ref[i] = TRQ_MAKE_REF(REF_SQUARE, i);
+                    ref[i] = TRQ_MAKE_REF(REF_SQUARE, nSqLeaf++);
                     break;
                 case TRQ_CUBE:
                     if (b.pIndex >= d->nCube) return trq::fail(TRQ_ERR_LAYOUT, "leaf %u: cube pIndex %u >= nCube %u", i, b.pIndex, d->nCube);
@@ -180,43 +224,86 @@ int plan_layout(const trq_scene_desc* d, std::vector<uint32_t>& ref, trq_scene_i
             }
         }
     }
+    // interior numbering: breadth-first block first, then the others in depth-first order
+    const uint32_t nInterior = (uint32_t)interiorDfs.size();
+    uint32_t nTop = 0;
+    if (nInterior) {
+        std::vector<uint32_t> bfs;
+        bfs.reserve(kTopMax);
+        bfs.push_back(0u);
+        for (size_t head = 0; head < bfs.size(); ++head) {
+            const RefBVH& b = N[bfs[head]];
+            if (bfs.size() < kTopMax && N[b.left].pType == TRQ_BVH) bfs.push_back(b.left);
+            if (bfs.size() < kTopMax && N[b.right].pType == TRQ_BVH) bfs.push_back(b.right);
+        }
+        nTop = (uint32_t)bfs.size();
+        for (uint32_t k = 0; k < nTop; ++k) ref[bfs[k]] = TRQ_MAKE_REF(REF_INTERIOR, k) | 0x10000000u;   // bit 28: numbered (cleared below)
+        uint32_t next = nTop;
+        for (uint32_t i : interiorDfs) {
+            if (ref[i] & 0x10000000u) ref[i] &= ~0x10000000u;
+            else ref[i] = TRQ_MAKE_REF(REF_INTERIOR, next++);
+        }
+    }
     info.nNode = n; info.nInterior = nInterior; info.nLeaf = nLeaf; info.maxDepth = maxDepth;
     info.nTri = nTriLeaf; info.nSphere = nSphLeaf;
     info.nSquare = d->nSquare; info.nCube = d->nCube;
+    info.topNodes = nTop;
     return TRQ_OK;
 }
 
-int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, trq_hit* d_hits, cudaStream_t st,
-                 const unsigned long long* nPtr = nullptr, const GatherDev* gather = nullptr) {
+// Which launch configuration a trace uses: TRQ_CFG in the environment (experiments), else the scene's default.
+int pick_cfg(const trq_scene* s) {
+    static const int env = [] { const char* e = getenv("TRQ_CFG"); return e ? atoi(e) : -1; }();
+    int c = (env >= 0 && env < kNumCfgs) ? env : s->defaultCfg;
+    if (!s->cfg[c].usable) c = 0;
+    return c;
+}
+
+// Peer fan-out of one trq_trace_gather step (see struct trq_gather below).
+struct GatherLaunch {
+    uint32_t nPeer = 0;
+    unsigned long long step = 0;
+    unsigned long long* ownFlag = nullptr; unsigned long long* ownCount = nullptr;
+    void* peerHits[TRQ_MAX_PEERS] = {};
+    unsigned long long* peerFlag[TRQ_MAX_PEERS] = {};
+    unsigned long long* peerCount[TRQ_MAX_PEERS] = {};
+};
+
+int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, void* d_hits, cudaStream_t st,
+                 const unsigned long long* nPtr = nullptr, const GatherLaunch* gather = nullptr) {
     if (n == 0 && !gather) return TRQ_OK;
+    const bool hit16 = (flags & TRQ_HIT16) != 0;
+    const size_t recBytes = hit16 ? sizeof(trq_hit16) : sizeof(trq_hit);
     constexpr uint64_t kMaxPerLaunch = 1ull << 31;             // the kernels keep a 32-bit ray index per lane
     if (n > kMaxPerLaunch) {
         if (nPtr || gather) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect / trq_trace_gather: more than 2^31 rays");
         for (uint64_t off = 0; off < n; off += kMaxPerLaunch) {
             const uint64_t m = (n - off) < kMaxPerLaunch ? (n - off) : kMaxPerLaunch;
-            const int rc = launch_trace(s, d_rays + off, m, flags, d_hits + off, st);
+            const int rc = launch_trace(s, d_rays + off, m, flags, (uint8_t*)d_hits + off * recBytes, st);
             if (rc != TRQ_OK) return rc;
         }
         return TRQ_OK;
     }
     const bool any = (flags & TRQ_TRACE_ANY) != 0;
-    unsigned long long* usedCounter = nullptr;
-    bool fused = false;
     cudaEvent_t* prof = nullptr;
     if (s->profile) {
-        prof = s->evProf[s->profHead % kProfRing];
-        s->profHead++; if (s->profCount < kProfRing) s->profCount++;
+        std::lock_guard<std::mutex> lock(s->profMutex);
+        if (s->profile) {
+            prof = s->evProf[s->profHead % kProfRing];
+            s->profHead++; if (s->profCount < kProfRing) s->profCount++;
+        }
     }
-    if (n == 0) {
-        // gather with an empty batch: nothing to trace, but the peers still wait for this rank's step
-    } else if (flags & TRQ_KERNEL_REFLAYOUT) {
+    if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));          // the ordering pass is part of the timed traversal
+    if (flags & TRQ_KERNEL_REFLAYOUT) {
+        if (hit16 || gather) return trq::fail(TRQ_ERR_INVALID, "TRQ_KERNEL_REFLAYOUT writes trq_hit records on one device only");
         const unsigned block = 128;
         const uint64_t grid = (n + block - 1) / block;
         if (grid > 0x7fffffffull) return trq::fail(TRQ_ERR_INVALID, "trq_trace: batch too large");
-        if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));
-        if (any) trace_reflayout_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr);
-        else     trace_reflayout_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr);
-        g_launches++;
+        if (any) trace_reflayout_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, (trq_hit*)d_hits, n, nPtr);
+        else     trace_reflayout_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, (trq_hit*)d_hits, n, nPtr);
+        if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
+        resolve_hits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->dev, d_rays, (trq_hit*)d_hits, n, nPtr);
+        g_launches += 2;
     } else {
         static const uint32_t refillMin = [] {
             const char* e = getenv("TRQ_REFILL_MIN");
@@ -229,24 +316,27 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
         static const int blocksPerSMOverride =[] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
-        const size_t smem = s->traceSmem;
-        // triangle-only scene (and no peer gather): the trace kernel writes final records, there is no resolve pass
-        static const int fusedEnv = [] { const char* e = getenv("TRQ_FUSED_RESOLVE"); return e ? atoi(e) : 1; }();
-        fused = s->allTriangles && !gather && fusedEnv != 0;
-        int perSM = s->blocksPerSM[any ? 1 : 0][fused ? 1 : 0];                  // queried once, in trq_scene_create
+        const int c = pick_cfg(s);
+        const KernelCfg& K = kCfgs[c];
+        const trq_scene::CfgState& cs = s->cfg[c];
+        int perSM = cs.blocksPerSM[any ? 1 : 0][hit16 ? 1 : 0];                  // queried once, in trq_scene_create
         if (blocksPerSMOverride > 0 && blocksPerSMOverride < perSM) perSM = blocksPerSMOverride;
         uint64_t grid = (uint64_t)perSM * (uint64_t)s->numSMs;             // persistent: a multiple of the SM count
-        const uint64_t need = (n + TRQ_BLOCK - 1) / TRQ_BLOCK;
+        const uint64_t need = n ? (n + K.block - 1) / K.block : 1;          // an empty gather step still publishes
         if (grid > need) grid = need;
-        // queue heads are zero at creation and re-zeroed by the resolve kernel that follows each trace on the stream
-        unsigned long long* counter = s->d_counters + (s->counterNext.fetch_add(1) % kCounterRing);
-        usedCounter = counter;
-        if (fused) TRQ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));   // no resolve kernel to re-zero it
-        TraceParams P;
-        P.rays = d_rays; P.hits = d_hits; P.n = n; P.counter = counter;
+        TraceParams P{};
+        P.rays = d_rays; P.hits = d_hits; P.n = n;
+        // the head is zero: heads are zeroed at creation and every launch's last CTA re-arms the one it used
+        P.queue = s->d_queues + (s->queueNext.fetch_add(1) % kQueueRing);
         P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
+        P.topCount = K.top ? cs.topCount : 0;
         P.order = nullptr; P.nPtr = nPtr;
-        if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));      // the ordering pass is part of the timed traversal
+        if (gather) {
+            P.nPeer = gather->nPeer; P.step = gather->step; P.ownFlag = gather->ownFlag; P.ownCount = gather->ownCount;
+            for (uint32_t k = 0; k < gather->nPeer; ++k) {
+                P.peerHits[k] = gather->peerHits[k]; P.peerFlag[k] = gather->peerFlag[k]; P.peerCount[k] = gather->peerCount[k];
+            }
+        }
         // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
         // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
         // that does not fit L2); TRQ_SORT_RAYS=0/1 in the environment overrides for experiments.
@@ -265,20 +355,11 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             g_launches += 3;
             P.order = order;
         }
-        if (any) { if (fused) trace_packed_kernel<true, true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
-                   else       trace_packed_kernel<true, false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P); }
-        else     { if (fused) trace_packed_kernel<false, true><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P);
-                   else       trace_packed_kernel<false, false><<<(unsigned)grid, TRQ_BLOCK, smem, st>>>(s->dev, P); }
+        void* args[2] = {(void*)&s->dev, (void*)&P};
+        TRQ_CUDA(cudaLaunchKernel(K.fn[any ? 1 : 0][hit16 ? 1 : 0], dim3((unsigned)grid), dim3((unsigned)K.block), args, cs.smem, st));
         g_launches++;
         if (scratch) TRQ_CUDA(cudaFreeAsync(scratch, st));
-    }
-    if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
-    if (!fused) {
-        const unsigned block = 256;
-        const uint64_t grid = n ? (n + block - 1) / block : 1;
-        if (gather) resolve_hits_kernel<true><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr, usedCounter, *gather);
-        else        resolve_hits_kernel<false><<<(unsigned)grid, block, 0, st>>>(s->dev, d_rays, d_hits, n, nPtr, usedCounter, GatherDev{});
-        g_launches++;
+        if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
     }
     if (prof) TRQ_CUDA(cudaEventRecord(prof[2], st));
     TRQ_CUDA(cudaGetLastError());
@@ -338,21 +419,35 @@ int ensure_staging(trq_scene* s, uint64_t chunk) {
 // Host-pointer path: the batch is cut into chunks; chunk k goes through staging buffer k % kStageBufs on that
 // buffer's own stream (copy in, trace, copy out, in stream order). Different chunks overlap on the two copy engines
 // and the SMs, buffer reuse is ordered by the stream itself, and a chunk costs four driver calls.
-int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits) {
+// A synchronous call pays one chunk of H2D before anything overlaps and one chunk of trace + D2H after the last copy
+// in; the chunk sizes therefore ramp up at the front and down at the back (1/8, 1/4, 1/2, 1, ..., 1, 1/2, 1/4, 1/8).
+int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, void* hits) {
     const uint64_t chunkRays = [] {                           // read per call so that one process can sweep it
         const char* e = getenv("TRQ_CHUNK_RAYS");
         long long v = e ? atoll(e) : (TRQ_DEFAULT_CHUNK_RAYS)  /* B200 sweep: profiles/r01_e2e_chunk_sweep.txt */;
         return (uint64_t)(v < 1024 ? 1024 : v);
     }();
+    static const int taperEnv = [] { const char* e = getenv("TRQ_CHUNK_TAPER"); return e ? atoi(e) : 1; }();
+    const size_t recBytes = (flags & TRQ_HIT16) ? sizeof(trq_hit16) : sizeof(trq_hit);
     std::lock_guard<std::mutex> lock(s->stageMutex);
     // a sorted chunk is only as coherent as it is large: C5 e2e 461 / 605 / 599 / 504 Mrays/s at 512K / 1M / 2M / 4M rays
     const uint64_t want = (flags & TRQ_SORT_RAYS) ? 2 * chunkRays : chunkRays;
     const uint64_t chunk = n < want ? n : want;
     int rc = ensure_staging(s, chunk);
     if (rc != TRQ_OK) return rc;
+    const bool taper = taperEnv && !(flags & (TRQ_SORT_RAYS | TRQ_HOST_ASYNC)) && n >= 6 * chunk && chunk >= 8192;
+    std::vector<uint64_t> sizes;
+    if (taper) {
+        const uint64_t ramp[3] = {chunk / 8, chunk / 4, chunk / 2};
+        uint64_t mid = n - 2 * (ramp[0] + ramp[1] + ramp[2]);
+        sizes.assign(ramp, ramp + 3);
+        while (mid) { const uint64_t m = mid < chunk ? mid : chunk; sizes.push_back(m); mid -= m; }
+        for (int r = 2; r >= 0; --r) sizes.push_back(ramp[r]);
+    } else {
+        for (uint64_t left = n; left; ) { const uint64_t m = left < chunk ? left : chunk; sizes.push_back(m); left -= m; }
+    }
     uint64_t done = 0;
-    while (done < n) {
-        const uint64_t m = (n - done) < chunk ? (n - done) : chunk;
+    for (const uint64_t m : sizes) {
         const int b = (int)(s->stageSeq++ % kStageBufs);       // runs across calls: TRQ_HOST_ASYNC calls share the ring
         cudaStream_t st = s->stageStream[b];
 #ifdef TRQ_STAGE_TIMELINE
@@ -367,7 +462,7 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, tr
 #ifdef TRQ_STAGE_TIMELINE
         cudaEventRecord(tl[2], st);
 #endif
-        TRQ_CUDA(cudaMemcpyAsync(hits + done, s->d_stageHits[b], m * sizeof(trq_hit), cudaMemcpyDeviceToHost, st));
+        TRQ_CUDA(cudaMemcpyAsync((uint8_t*)hits + done * recBytes, s->d_stageHits[b], m * recBytes, cudaMemcpyDeviceToHost, st));
 #ifdef TRQ_STAGE_TIMELINE
         cudaEventRecord(tl[3], st);
 #endif
@@ -413,7 +508,8 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
 
     trq_scene_info_t info{};
     std::vector<uint32_t> ref;
-    int rc = plan_layout(d, ref, info);                        // pure host validation: runs without a GPU
+    uint32_t maxPIndex = 0;
+    int rc = plan_layout(d, ref, info, maxPIndex);             // pure host validation: runs without a GPU
     if (rc != TRQ_OK) return rc;
 
     int ndev = trq_device_count();
@@ -426,6 +522,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     trq_scene* s = new (std::nothrow) trq_scene();
     if (!s) return trq::fail(TRQ_ERR_NOMEM, "trq_scene_create: out of host memory");
     s->device = device;
+    s->maxPIndex = maxPIndex;
     auto bail = [&](int code) { free_scene(s); return code; };
 
     cudaDeviceProp prop;
@@ -444,18 +541,22 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     auto bail2 = [&](int code) { cudaFree(d_ref); return bail(code); };
 
     const size_t nodeBytes = (size_t)info.nInterior * 64, triBytes = (size_t)info.nTri * 16 * TRQ_TRI_STRIDE, sphBytes = (size_t)info.nSphere * 32;
+    uint32_t nSqLeaf = 0;
+    for (uint32_t r : ref) if (r != TRQ_REF_DONE_WORD && TRQ_REF_KIND(r) == REF_SQUARE) ++nSqLeaf;
+    const size_t sqBytes = (size_t)nSqLeaf * 16 * TRQ_SQ_STRIDE;
     if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes));
     if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes));
     if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes));
+    if (sqBytes && cudaMalloc((void**)&s->d_sq, sqBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(squares %zu B) failed", sqBytes));
     const size_t triNBytes = (size_t)info.nTri * 64;
     if (triNBytes && cudaMalloc((void**)&s->d_triN, triNBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(triangle normals %zu B) failed", triNBytes));
-    if (cudaMalloc((void**)&s->d_counters, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(counters) failed"));
-    if (cudaMemset(s->d_counters, 0, kCounterRing * sizeof(unsigned long long)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMemset(counters) failed"));
+    if (cudaMalloc((void**)&s->d_queues, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(queue heads) failed"));
+    if (cudaMemset(s->d_queues, 0, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMemset(queue heads) failed"));
 
     {
         const unsigned block = 256, grid = (d->nNode + block - 1) / block;
-        pack_scene_kernel<<<grid, block>>>(s->d_bvh, d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres,
-                                           s->d_nodes, s->d_tris, s->d_sph, s->d_triN);
+        pack_scene_kernel<<<grid, block>>>(s->d_bvh, d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres, s->d_squares,
+                                           s->d_nodes, s->d_tris, s->d_sph, s->d_sq, s->d_triN);
         g_launches++;
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "pack_scene_kernel failed: %s", cudaGetErrorString(e)));
@@ -465,8 +566,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     const RefBVH* N = (const RefBVH*)d->bvhList;
     s->dev.spheres = s->d_spheres; s->dev.squares = s->d_squares; s->dev.cubes = s->d_cubes;
     s->dev.verts = s->d_verts; s->dev.idx = s->d_idx; s->dev.bvh = s->d_bvh;
-    s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.sph = s->d_sph; s->dev.triN = s->d_triN;
-    s->allTriangles = info.nTri > 0 && info.nTri == info.nLeaf;
+    s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.sph = s->d_sph; s->dev.sq = s->d_sq; s->dev.triN = s->d_triN;
     s->dev.rootRef = ref[0];
     for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = N[0].bBOX.mini[k]; s->dev.rootMax[k] = N[0].bBOX.maxi[k]; }
     s->dev.nNode = d->nNode;
@@ -482,26 +582,40 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
         if (e == cudaSuccess) e = cudaMemPoolSetAttribute(s->scratchPool, cudaMemPoolAttrReleaseThreshold, &keep);
         if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(e)));
     }
-    s->traceSmem = ((size_t)s->stackDepth + COLD_WORDS) * TRQ_BLOCK * sizeof(uint32_t);
-    {
+    // launch configurations: per-CTA shared memory = staged top-of-tree nodes + far-child stack + cold per-ray words
+    for (int c = 0; c < kNumCfgs; ++c) {
+        const KernelCfg& K = kCfgs[c];
+        trq_scene::CfgState& cs = s->cfg[c];
+        const size_t perRay = ((size_t)s->stackDepth + COLD_WORDS) * K.block * sizeof(uint32_t);
+        size_t budget = kSmemPerSM / (size_t)K.minb - kSmemBlockReserve;
+        if (budget > kSmemPerBlockMax) budget = kSmemPerBlockMax;
+        cs.topCount = 0;
+        if (K.top) {
+            static const int topEnv = [] { const char* e = getenv("TRQ_TOP_NODES"); return e ? atoi(e) : -1; }();
+            if (budget > perRay) cs.topCount = (uint32_t)((budget - perRay) / 64);
+            if (cs.topCount > info.topNodes) cs.topCount = info.topNodes;
+            if (topEnv >= 0 && (uint32_t)topEnv < cs.topCount) cs.topCount = (uint32_t)topEnv;
+        }
+        cs.smem = perRay + (size_t)cs.topCount * 64;
+        cs.usable = cs.smem <= kSmemPerBlockMax && !(K.top && cs.topCount == 0 && c != 0);
+        if (!cs.usable) continue;
         cudaError_t e = cudaSuccess;
-        const void* variants[2][2] = {{(const void*)trace_packed_kernel<false, false>, (const void*)trace_packed_kernel<false, true>},
-                                      {(const void*)trace_packed_kernel<true, false>, (const void*)trace_packed_kernel<true, true>}};
-        for (int a = 0; a < 2; ++a)
-            for (int f = 0; f < 2; ++f) {
-                if (e == cudaSuccess && s->traceSmem > 48 * 1024)
-                    e = cudaFuncSetAttribute(variants[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->traceSmem);
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocksPerSM[a][f], variants[a][f], TRQ_BLOCK, s->traceSmem);
+        for (int a = 0; a < 2 && e == cudaSuccess; ++a)
+            for (int f = 0; f < 2 && e == cudaSuccess; ++f) {
+                if (cs.smem > 48 * 1024) e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerBlockMax);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs.blocksPerSM[a][f], K.fn[a][f], K.block, cs.smem);
+                if (e == cudaSuccess && cs.blocksPerSM[a][f] < 1) cs.usable = false;
             }
-        if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel occupancy query failed: %s", cudaGetErrorString(e)));
-        if (s->blocksPerSM[0][0] < 1 || s->blocksPerSM[0][1] < 1 || s->blocksPerSM[1][0] < 1 || s->blocksPerSM[1][1] < 1)
-            return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->traceSmem));
+        if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel (%s) occupancy query failed: %s", K.name, cudaGetErrorString(e)));
     }
+    if (!s->cfg[0].usable) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->cfg[0].smem));
+    s->autoCfg = 0;
+    s->defaultCfg = s->autoCfg;
 
     info.bytesReferenceLayout = (uint64_t)d->nSphere * sizeof(RefSphere) + (uint64_t)d->nSquare * sizeof(RefSquare) +
                                 (uint64_t)d->nCube * sizeof(RefCube) + (uint64_t)d->nVert * sizeof(RefVertex) +
                                 (uint64_t)d->nTri * 12 + (uint64_t)d->nNode * sizeof(RefBVH);
-    info.bytesPacked = nodeBytes + triBytes + sphBytes + triNBytes;
+    info.bytesPacked = nodeBytes + triBytes + sphBytes + sqBytes + triNBytes;
     info.device = device;
     s->info = info;
     *out = s;
@@ -512,6 +626,20 @@ int trq_scene_destroy(trq_scene* s) {
     if (!s) return TRQ_OK;
     DeviceGuard guard(s->device);
     free_scene(s);
+    return TRQ_OK;
+}
+
+int trq_kernel_config_count(void) { return kNumCfgs; }
+
+const char* trq_kernel_config_name(int cfg) { return (cfg >= 0 && cfg < kNumCfgs) ? kCfgs[cfg].name : nullptr; }
+
+int trq_scene_set_kernel_config(trq_scene* s, int cfg, uint32_t* topNodesStaged) {
+    if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_scene_set_kernel_config: NULL scene");
+    if (cfg < 0) cfg = s->autoCfg;
+    if (cfg >= kNumCfgs) return trq::fail(TRQ_ERR_INVALID, "trq_scene_set_kernel_config: %d configurations", kNumCfgs);
+    if (!s->cfg[cfg].usable) return trq::fail(TRQ_ERR_INVALID, "trq_scene_set_kernel_config: configuration %s does not fit this scene (stack depth %u)", kCfgs[cfg].name, s->stackDepth);
+    s->defaultCfg = cfg;
+    if (topNodesStaged) *topNodesStaged = kCfgs[cfg].top ? s->cfg[cfg].topCount : 0;
     return TRQ_OK;
 }
 
@@ -528,6 +656,7 @@ int trq_profile_enable(trq_scene* s, int on) {
         for (int k = 0; k < kProfRing; ++k)
             for (int j = 0; j < 3; ++j) TRQ_CUDA(cudaEventCreate(&s->evProf[k][j]));
     }
+    std::lock_guard<std::mutex> lock(s->profMutex);
     s->profile = on != 0;
     s->profHead = 0; s->profCount = 0;
     return TRQ_OK;
@@ -536,6 +665,7 @@ int trq_profile_enable(trq_scene* s, int on) {
 int trq_profile_read(trq_scene* s, uint32_t* nLaunches, float* traceMs, float* resolveMs) {
     if (!s || !nLaunches || !traceMs || !resolveMs) return trq::fail(TRQ_ERR_INVALID, "trq_profile_read: NULL argument");
     DeviceGuard guard(s->device);
+    std::lock_guard<std::mutex> lock(s->profMutex);
     *nLaunches = 0; *traceMs = 0.0f; *resolveMs = 0.0f;
     for (uint32_t k = 0; k < s->profCount; ++k) {
         cudaEvent_t* ev = s->evProf[(s->profHead - 1 - k) % kProfRing];
@@ -549,12 +679,14 @@ int trq_profile_read(trq_scene* s, uint32_t* nLaunches, float* traceMs, float* r
     return TRQ_OK;
 }
 
-int trq_trace(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits, void* stream) {
+int trq_trace(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, void* hits, void* stream) {
     if (!s) return trq::fail(TRQ_ERR_INVALID, "trq_trace: NULL scene");
     if (n == 0) return TRQ_OK;
     if (!rays || !hits) return trq::fail(TRQ_ERR_INVALID, "trq_trace: NULL rays/hits");
-    if (!(flags & TRQ_HOST_PTRS) && ((((uintptr_t)rays) | ((uintptr_t)hits)) & 31u))
-        return trq::fail(TRQ_ERR_INVALID, "trq_trace: device rays/hits must be 32-byte aligned (one record = one 256-bit access)");
+    if ((flags & TRQ_HIT16) && s->maxPIndex >= (1u << 28))
+        return trq::fail(TRQ_ERR_INVALID, "trq_trace: TRQ_HIT16 packs pIndex into 28 bits; this scene has pIndex up to %u", s->maxPIndex);
+    if (!(flags & TRQ_HOST_PTRS) && ((((uintptr_t)rays) & 31u) || (((uintptr_t)hits) & ((flags & TRQ_HIT16) ? 15u : 31u))))
+        return trq::fail(TRQ_ERR_INVALID, "trq_trace: device rays / hits must be aligned to their record size (32 / 32 or 16 bytes: one access per record)");
     DeviceGuard guard(s->device);
     if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
     if (flags & TRQ_HOST_PTRS) return trace_host(s, rays, n, flags, hits);
@@ -716,15 +848,17 @@ int trq_spawn_shadow_rng(trq_scene* s, const trq_ray* rays, const trq_hit* hits,
 
 // ---------------------------------------------------------------------------------------------------------
 // Peer-memory hit gather (a consumer that wants every rank's hits whole). One process per GPU;
-// every rank owns a buffer [parity][rank][capacity] of trq_hit plus a small header (flags, counts), exported through
-// CUDA IPC. trq_trace_gather traces this rank's rays and its resolve kernel stores each finished record into slot
-// [rank] of EVERY rank's buffer over NVLink -- the all-gather is fused into the kernel that produces the records, no
-// NCCL call and no second pass over the data -- then publishes (count, step) with system-scope release stores.
-// trq_gather_wait enqueues a small kernel that acquires all ranks' step numbers. Two parities: a rank can run one
-// step ahead of a peer that is still consuming the previous one, never two (it would need the peer's next flag).
+// every rank owns a buffer [phase][rank][capacity] of trq_hit plus a small header (flags, counts), exported through
+// CUDA IPC. trq_trace_gather traces this rank's rays and the trace kernel itself stores each finished record into slot
+// [rank] of EVERY rank's buffer over NVLink as the ray retires -- compute and all-gather are one kernel, the transfer
+// runs under the traversal, no NCCL call and no second pass over the data -- then its last CTA publishes (count, step)
+// with system-scope release stores. trq_gather_wait enqueues a small kernel that acquires all ranks' step numbers.
+// Three phases (step mod 3): a peer can start writing phase p again at step k + 3 only after it has seen this rank's
+// flag for step k + 2, so the result of step k stays valid until this rank's trq_trace_gather for step k + 2 executes.
 namespace {
-constexpr size_t kGatherHeader = 4096;                 // flags[16] u64 @0, counts[2][16] u64 @128, blocksDone u32 @2048
-constexpr size_t kGatherCountsAt = 128, kGatherBlocksDoneAt = 2048;
+constexpr size_t kGatherHeader = 4096;                 // flags[16] u64 @0, counts[3][16] u64 @128
+constexpr size_t kGatherCountsAt = 128;
+constexpr unsigned kGatherPhases = 3;
 }
 
 struct trq_gather {
@@ -736,9 +870,10 @@ struct trq_gather {
     unsigned int* h_status = nullptr;                  // pinned + mapped: raised by gather_wait_kernel on timeout
     unsigned int* d_status = nullptr;
     unsigned long long step = 0;
+    uint32_t lastFlags = 0;
     bool connected = false;
-    size_t slot_offset(unsigned parity, uint32_t r) const {
-        return kGatherHeader + ((size_t)parity * world + r) * capacity * sizeof(trq_hit);
+    size_t slot_offset(unsigned phase, uint32_t r) const {
+        return kGatherHeader + ((size_t)phase * world + r) * capacity * sizeof(trq_hit);
     }
 };
 
@@ -756,7 +891,7 @@ int trq_gather_create(trq_scene* s, uint32_t rank, uint32_t world, uint64_t capa
     trq_gather* g = new (std::nothrow) trq_gather();
     if (!g) return trq::fail(TRQ_ERR_NOMEM, "trq_gather_create: out of host memory");
     g->scene = s; g->rank = rank; g->world = world; g->capacity = capacity;
-    const size_t total = kGatherHeader + 2 * (size_t)world * capacity * sizeof(trq_hit);
+    const size_t total = kGatherHeader + (size_t)kGatherPhases * world * capacity * sizeof(trq_hit);
     cudaError_t e = cudaMalloc((void**)&g->base, total);
     if (e == cudaSuccess) e = cudaMemset(g->base, 0, kGatherHeader);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -793,31 +928,32 @@ int trq_gather_connect(trq_gather* g, const void* handles) {
 int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t n, uint32_t flags, void* stream) {
     if (!s || !g || g->scene != s) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: NULL or foreign scene / gather");
     if (!g->connected) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: call trq_gather_connect first");
-    if (flags & (TRQ_HOST_PTRS | TRQ_HOST_ASYNC)) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: device pointers only");
+    if (flags & (TRQ_HOST_PTRS | TRQ_HOST_ASYNC | TRQ_KERNEL_REFLAYOUT)) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: device pointers and the packed kernel only");
     if (n > g->capacity) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: %llu rays exceed the capacity %llu", (unsigned long long)n, (unsigned long long)g->capacity);
     if (n && !rays) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: NULL rays");
     if (((uintptr_t)rays) & 31u) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: rays must be 32-byte aligned");
+    if ((flags & TRQ_HIT16) && s->maxPIndex >= (1u << 28)) return trq::fail(TRQ_ERR_INVALID, "trq_trace_gather: TRQ_HIT16 packs pIndex into 28 bits");
     DeviceGuard guard(s->device);
     if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
     const unsigned long long step = ++g->step;
-    const unsigned parity = (unsigned)(step & 1ull);
-    GatherDev G{};
+    const unsigned phase = (unsigned)(step % kGatherPhases);
+    g->lastFlags = flags;
+    GatherLaunch G;
     G.step = step;
-    G.blocksDone = (unsigned int*)(g->base + kGatherBlocksDoneAt);
     G.ownFlag = (unsigned long long*)g->base + g->rank;
-    G.ownCount = (unsigned long long*)(g->base + kGatherCountsAt) + parity * TRQ_GATHER_MAX_RANKS + g->rank;
+    G.ownCount = (unsigned long long*)(g->base + kGatherCountsAt) + phase * TRQ_GATHER_MAX_RANKS + g->rank;
     for (uint32_t r = 0; r < g->world; ++r) {
         if (r == g->rank) continue;
         const uint32_t k = G.nPeer++;
-        G.peerSlot[k] = (trq_hit*)(g->peerBase[r] + g->slot_offset(parity, g->rank));
+        G.peerHits[k] = g->peerBase[r] + g->slot_offset(phase, g->rank);
         G.peerFlag[k] = (unsigned long long*)g->peerBase[r] + g->rank;
-        G.peerCount[k] = (unsigned long long*)(g->peerBase[r] + kGatherCountsAt) + parity * TRQ_GATHER_MAX_RANKS + g->rank;
+        G.peerCount[k] = (unsigned long long*)(g->peerBase[r] + kGatherCountsAt) + phase * TRQ_GATHER_MAX_RANKS + g->rank;
     }
-    trq_hit* own = (trq_hit*)(g->base + g->slot_offset(parity, g->rank));
+    void* own = g->base + g->slot_offset(phase, g->rank);
     return launch_trace(s, rays, n, flags, own, (cudaStream_t)stream, nullptr, &G);
 }
 
-int trq_gather_wait(trq_gather* g, void* stream, const trq_hit** hitsAll, const uint64_t** counts) {
+int trq_gather_wait(trq_gather* g, void* stream, const void** hitsAll, const uint64_t** counts) {
     if (!g) return trq::fail(TRQ_ERR_INVALID, "trq_gather_wait: NULL gather");
     if (g->step == 0) return trq::fail(TRQ_ERR_INVALID, "trq_gather_wait: nothing traced yet");
     DeviceGuard guard(g->scene->device);
@@ -828,9 +964,9 @@ int trq_gather_wait(trq_gather* g, void* stream, const trq_hit** hitsAll, const 
     gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)g->base, g->world, g->step, timeoutNs, g->d_status);
     g_launches++;
     TRQ_CUDA(cudaGetLastError());
-    const unsigned parity = (unsigned)(g->step & 1ull);
-    if (hitsAll) *hitsAll = (const trq_hit*)(g->base + g->slot_offset(parity, 0));
-    if (counts) *counts = (const uint64_t*)(g->base + kGatherCountsAt) + parity * TRQ_GATHER_MAX_RANKS;
+    const unsigned phase = (unsigned)(g->step % kGatherPhases);
+    if (hitsAll) *hitsAll = g->base + g->slot_offset(phase, 0);
+    if (counts) *counts = (const uint64_t*)(g->base + kGatherCountsAt) + phase * TRQ_GATHER_MAX_RANKS;
     return TRQ_OK;
 }
 

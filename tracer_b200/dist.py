@@ -194,8 +194,9 @@ class _DevArray:
 
 
 class HitGather:
-    """Hit all-gather fused into the resolve kernel (trq_trace_gather): every rank's records land in every rank's
-    (world, capacity, 8) buffer through NVLink peer stores. One process per GPU on one node.
+    """Hit all-gather fused into the traversal kernel (trq_trace_gather): every rank's records land in every rank's
+    (world, capacity, 8) buffer through NVLink peer stores issued as the rays retire. One process per GPU on one node
+    (two ranks may share one device for tests: CUDA IPC works between processes on the same GPU).
 
         g = HitGather(scene, capacity)          # collective: allocates, exchanges CUDA-IPC handles, connects
         g.trace(rays); hits_all, counts = g.wait()      # every rank, every step; hits_all[r, :counts[r]]
@@ -230,20 +231,24 @@ class HitGather:
                 self._h = None
             raise RuntimeError(f"{what} failed on {'this rank: ' + msg if rc != 0 else 'another rank'}")
 
-    def trace(self, rays, any=False, sort=False, stream=None):
-        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
+    def trace(self, rays, any=False, sort=False, stream=None, hit16=False):
+        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0) | (L.HIT16 if hit16 else 0)
+        self._hit16 = bool(hit16)
         self._check(self._lib.trq_trace_gather(self.scene._h, self._h, rays.data_ptr(), rays.shape[0], flags, self.scene._stream(stream)),
                     "trq_trace_gather")
 
     def wait(self, stream=None):
         """Enqueues the wait for every rank's records of the last trace(); returns ((world, capacity, 8) float32 view of the
-        local buffer, (world,) int64 view of the per-rank counts). Both are valid until the next-but-one trace()."""
+        local buffer, (world,) int64 view of the per-rank counts). Both are valid until the next-but-one trace() executes
+        (three buffer phases). After trace(hit16=True) the view is (world, capacity, 4): trq_hit16 rows."""
         import ctypes as C
         import torch
         hp, cp = C.c_void_p(), C.c_void_p()
         self._check(self._lib.trq_gather_wait(self._h, self.scene._stream(stream), C.byref(hp), C.byref(cp)), "trq_gather_wait")
         dev = torch.device("cuda", self.scene.device)
         hits = torch.as_tensor(_DevArray(hp.value, (self.world, self.capacity, 8), "<f4"), device=dev)
+        if getattr(self, "_hit16", False):                       # 16-byte records at the front of each 32-byte-stride slot
+            hits = hits.view(self.world, self.capacity * 2, 4)[:, : self.capacity]
         counts = torch.as_tensor(_DevArray(cp.value, (self.world,), "<i8"), device=dev)
         return hits, counts
 

@@ -54,6 +54,10 @@ hit_dtype = np.dtype([
     ("u", "<f4"), ("v", "<f4"), ("material", "<u4"), ("flags", "<u4"),
 ])
 
+# trq_hit16: id = 0xffffffff on a miss, else front << 31 | pType << 28 | pIndex
+hit16_dtype = np.dtype([("t", "<f4"), ("id", "<u4"), ("u", "<f4"), ("v", "<f4")])
+HIT16_MISS = 0xFFFFFFFF
+
 record_dtype = np.dtype([
     ("hit", "<u4"), ("t", "<f4"), ("p", "<f4", 3), ("gn", "<f4", 3), ("sn", "<f4", 3),
     ("uv", "<f4", 2), ("front", "<u4"), ("material", "<u4"), ("pad", "<u4"),
@@ -61,12 +65,22 @@ record_dtype = np.dtype([
 
 assert bvh_dtype.itemsize == 64 and vertex_dtype.itemsize == 32
 assert sphere_dtype.itemsize == 272 and square_dtype.itemsize == 272 and cube_dtype.itemsize == 240
-assert ray_dtype.itemsize == 32 and hit_dtype.itemsize == 32 and record_dtype.itemsize == 64
+assert ray_dtype.itemsize == 32 and hit_dtype.itemsize == 32 and hit16_dtype.itemsize == 16 and record_dtype.itemsize == 64
 
 HIT_FLAG_HIT, HIT_FLAG_FRONT = 1, 2
-TRACE_ANY, HOST_PTRS, KERNEL_REFLAYOUT, SORT_RAYS, HOST_ASYNC = 0x1, 0x2, 0x4, 0x8, 0x10
+TRACE_ANY, HOST_PTRS, KERNEL_REFLAYOUT, SORT_RAYS, HOST_ASYNC, HIT16 = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 
 FLT_MAX = float(np.finfo(np.float32).max)
 FLT_MIN = float(np.finfo(np.float32).tiny)
 
 IDENTITY4 = np.eye(4, dtype=np.float32).reshape(16)   # column-major == row-major for identity
+
+
+def pack_hit16(hits):
+    """hit_dtype array -> the hit16_dtype array TRQ_HIT16 produces for the same rays (host restatement, for tests)."""
+    out = np.zeros(hits.shape, dtype=hit16_dtype)
+    hit = (hits["flags"] & HIT_FLAG_HIT) != 0
+    front = ((hits["flags"] & HIT_FLAG_FRONT) != 0).astype(np.uint32)
+    out["t"], out["u"], out["v"] = hits["t"], hits["u"], hits["v"]
+    out["id"] = np.where(hit, (front << 31) | (hits["pType"].astype(np.uint32) << 28) | (hits["pIndex"] & 0x0FFFFFFF), HIT16_MISS)
+    return out

@@ -115,7 +115,7 @@ class Scene:
         self.device = int(device)
         info = SceneInfo()
         check(lib.trq_scene_info(self._h, C.byref(info)), "trq_scene_info")
-        self.info = {k: getattr(info, k) for k, _ in SceneInfo._fields_ if k != "pad"}
+        self.info = {k: getattr(info, k) for k, _ in SceneInfo._fields_}
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -125,15 +125,17 @@ class Scene:
     __del__ = close
 
     # ---- Scene::hit over a batch ------------------------------------------------------------
-    def hit(self, rays, any=False, out=None, reflayout=False, stream=None, sort=False):
+    def hit(self, rays, any=False, out=None, reflayout=False, stream=None, sort=False, hit16=False):
         """rays: torch CUDA float32 tensor (n, 8) -> returns torch CUDA float32 tensor (n, 8) holding
-        trq_hit rows (view as int32 for the id fields); or numpy `ray_dtype` array -> numpy `hit_dtype`."""
-        flags = (L.TRACE_ANY if any else 0) | (L.KERNEL_REFLAYOUT if reflayout else 0) | (L.SORT_RAYS if sort else 0)
+        trq_hit rows (view as int32 for the id fields); or numpy `ray_dtype` array -> numpy `hit_dtype`.
+        hit16=True: the 16-byte trq_hit16 records instead ((n, 4) float32 tensor / `hit16_dtype` array)."""
+        flags = (L.TRACE_ANY if any else 0) | (L.KERNEL_REFLAYOUT if reflayout else 0) | (L.SORT_RAYS if sort else 0) | (L.HIT16 if hit16 else 0)
+        width = 4 if hit16 else 8
         if isinstance(rays, np.ndarray):
             if rays.dtype != L.ray_dtype:
                 raise TypeError("host rays must have ray_dtype")
             rays = np.ascontiguousarray(rays)
-            hits = out if out is not None else np.empty(rays.size, dtype=L.hit_dtype)
+            hits = out if out is not None else np.empty(rays.size, dtype=L.hit16_dtype if hit16 else L.hit_dtype)
             check(lib.trq_trace(self._h, rays.ctypes.data, rays.size, flags | L.HOST_PTRS, hits.ctypes.data, None), "trq_trace")
             return hits
         import torch
@@ -142,17 +144,29 @@ class Scene:
         if rays.device.index != self.device:
             raise ValueError("rays are on a different device than the scene")
         n = rays.shape[0]
-        hits = out if out is not None else torch.empty((n, 8), dtype=torch.float32, device=rays.device)
+        hits = out if out is not None else torch.empty((n, width), dtype=torch.float32, device=rays.device)
         st = stream if stream is not None else torch.cuda.current_stream(rays.device).cuda_stream
         check(lib.trq_trace(self._h, rays.data_ptr(), n, flags, hits.data_ptr(), C.c_void_p(st)), "trq_trace")
         return hits
 
+    @staticmethod
+    def kernel_configs():
+        """Names of the traversal kernel's launch configurations ("<CTA size>x<CTAs per SM><top of tree staged>")."""
+        return [lib.trq_kernel_config_name(i).decode() for i in range(lib.trq_kernel_config_count())]
+
+    def set_kernel_config(self, cfg=-1):
+        """Selects a launch configuration (index; -1 = the library's choice). Returns the number of top-of-tree nodes that
+        configuration stages in shared memory for this scene. Results are identical in every configuration."""
+        staged = C.c_uint32(0)
+        check(lib.trq_scene_set_kernel_config(self._h, int(cfg), C.byref(staged)), "trq_scene_set_kernel_config")
+        return staged.value
+
     def host_sync(self):
         check(lib.trq_host_sync(self._h), "trq_host_sync")
 
-    def hit_host(self, rays_ptr, n, hits_ptr, any=False, sort=False, asynchronous=False):
+    def hit_host(self, rays_ptr, n, hits_ptr, any=False, sort=False, asynchronous=False, hit16=False):
         """Raw host-pointer call (pinned buffers owned by the caller); used by the e2e bench."""
-        flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS | (L.SORT_RAYS if sort else 0) | (L.HOST_ASYNC if asynchronous else 0)
+        flags = (L.TRACE_ANY if any else 0) | L.HOST_PTRS | (L.SORT_RAYS if sort else 0) | (L.HOST_ASYNC if asynchronous else 0) | (L.HIT16 if hit16 else 0)
         check(lib.trq_trace(self._h, rays_ptr, n, flags, hits_ptr, None), "trq_trace")
 
     # ---- wavefront callers (device tensors only) ----------------------------------------------
@@ -170,11 +184,11 @@ class Scene:
         check(lib.trq_cast_rays(self._h, C.byref(cam), W, H, rays.data_ptr(), self._stream(stream)), "trq_cast_rays")
         return rays
 
-    def hit_indirect(self, rays, count, any=False, out=None, sort=False, stream=None):
+    def hit_indirect(self, rays, count, any=False, out=None, sort=False, stream=None, hit16=False):
         """Scene::hit over min(*count, len(rays)) rays; `count` is a 1-element int64 CUDA tensor written by spawn_*."""
         import torch
-        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
-        hits = out if out is not None else torch.empty((rays.shape[0], 8), dtype=torch.float32, device=rays.device)
+        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0) | (L.HIT16 if hit16 else 0)
+        hits = out if out is not None else torch.empty((rays.shape[0], 4 if hit16 else 8), dtype=torch.float32, device=rays.device)
         check(lib.trq_trace_indirect(self._h, rays.data_ptr(), count.data_ptr(), rays.shape[0], flags, hits.data_ptr(),
                                      self._stream(stream)), "trq_trace_indirect")
         return hits
