@@ -9,7 +9,7 @@ import pytest
 
 from tracer_b200 import layout as L
 
-from test_gpu_parity import _torch, assert_hits_equal, gpu_trace
+from .test_gpu_parity import _torch, assert_hits_equal, gpu_trace
 
 pytestmark = pytest.mark.gpu
 

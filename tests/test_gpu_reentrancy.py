@@ -9,7 +9,7 @@ import pytest
 
 from tracer_b200 import layout as L
 
-from test_gpu_parity import _torch
+from .test_gpu_parity import _torch
 
 pytestmark = pytest.mark.gpu
 

@@ -56,6 +56,7 @@ constexpr int kStageBufs = 4;
 constexpr int kProfRing = 64;
 constexpr uint32_t kTopMax = 2047;         // interior nodes numbered breadth-first at the front (11 full levels)
 constexpr size_t kSmemPerSM = 228u * 1024u, kSmemPerBlockMax = 227u * 1024u, kSmemBlockReserve = 1024u;
+constexpr size_t kSmemDynamicMax = kSmemPerBlockMax - 1024u;   // dynamic part: the kernel also has a few static bytes (mbarrier)
 
 // Launch configurations of trace_packed_kernel: CTA size x resident CTAs per SM, with or without the top of the tree
 // staged in shared memory. [any][record format] -> kernel.
@@ -588,7 +589,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
         trq_scene::CfgState& cs = s->cfg[c];
         const size_t perRay = ((size_t)s->stackDepth + COLD_WORDS) * K.block * sizeof(uint32_t);
         size_t budget = kSmemPerSM / (size_t)K.minb - kSmemBlockReserve;
-        if (budget > kSmemPerBlockMax) budget = kSmemPerBlockMax;
+        if (budget > kSmemDynamicMax) budget = kSmemDynamicMax;
         cs.topCount = 0;
         if (K.top) {
             static const int topEnv = [] { const char* e = getenv("TRQ_TOP_NODES"); return e ? atoi(e) : -1; }();
@@ -597,16 +598,20 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
             if (topEnv >= 0 && (uint32_t)topEnv < cs.topCount) cs.topCount = (uint32_t)topEnv;
         }
         cs.smem = perRay + (size_t)cs.topCount * 64;
-        cs.usable = cs.smem <= kSmemPerBlockMax && !(K.top && cs.topCount == 0 && c != 0);
+        cs.usable = cs.smem <= kSmemDynamicMax && !(K.top && cs.topCount == 0 && c != 0);
         if (!cs.usable) continue;
         cudaError_t e = cudaSuccess;
         for (int a = 0; a < 2 && e == cudaSuccess; ++a)
             for (int f = 0; f < 2 && e == cudaSuccess; ++f) {
-                if (cs.smem > 48 * 1024) e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPerBlockMax);
+                if (cs.smem > 48 * 1024) e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDynamicMax);
                 if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs.blocksPerSM[a][f], K.fn[a][f], K.block, cs.smem);
                 if (e == cudaSuccess && cs.blocksPerSM[a][f] < 1) cs.usable = false;
             }
-        if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel (%s) occupancy query failed: %s", K.name, cudaGetErrorString(e)));
+        if (e != cudaSuccess) {
+            if (c == 0) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel (%s) occupancy query failed: %s", K.name, cudaGetErrorString(e)));
+            cudaGetLastError();                                // an optional configuration that does not fit: not offered
+            cs.usable = false;
+        }
     }
     if (!s->cfg[0].usable) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->cfg[0].smem));
     s->autoCfg = 0;
