@@ -57,6 +57,8 @@ struct SceneDev {
     const uint32_t*  idx;
     const RefBVH*    bvh;
     const float4*    nodes;     // 4 per interior node
+    const float4*    topSoA;    // [4][topStride]: the first topStride interior nodes again, quarter-major (smem staging source)
+    uint32_t         topStride;
     const float4*    tris;      // 3 per triangle leaf
     const float4*    sph;       // 2 per sphere leaf
     const float4*    sq;        // 4 per square leaf

@@ -261,6 +261,8 @@ struct TraceParams {
     uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
     uint32_t       topCount;       // interior nodes [0, topCount) are staged in shared memory (TOP kernels), else 0
+    uint32_t       swapMin;        // NEXT kernels: idle lanes swap in their prefetched ray when this many are idle
+    uint32_t       pad0;
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
     // Peer fan-out (trq_trace_gather): every finished record is also stored at the same index of nPeer remote buffers
@@ -385,20 +387,25 @@ enum : uint32_t { COLD_TEST_T = 0, COLD_BEST, COLD_U, COLD_V, COLD_AUX, COLD_RAY
 __device__ unsigned long long g_stats[8];
 #endif
 
-// Top-of-tree staging (TOP kernels): one TMA bulk copy (cp.async.bulk, completion on an mbarrier) brings the first
-// topCount packed nodes -- the top levels of the tree in breadth-first order -- into shared memory when the CTA starts.
-__device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src, uint32_t bytes, unsigned long long* mbar) {
+// Top-of-tree staging (TOP kernels): TMA bulk copies (cp.async.bulk, completion on an mbarrier) bring the first topCount
+// packed nodes -- the top levels of the tree in breadth-first order -- into shared memory when the CTA starts. Source and
+// destination are quarter-major ([4][n] float4: all q0, then all q1, ...): with the node-major 64-byte stride every q0
+// would sit in banks 0-3 / 16-19 and a warp's LDS.128 would serialise 4 ways.
+__device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src, uint32_t count, uint32_t srcStride, unsigned long long* mbar) {
     const uint32_t mb = (uint32_t)__cvta_generic_to_shared(mbar);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (bytes == 0) return;
+    if (count == 0) return;
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"(mb) : "memory");
+        const uint32_t bytes = count * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(4u * bytes) : "memory");
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(dst + (size_t)q * count)), "l"(src + (size_t)q * srcStride), "r"(bytes), "r"(mb) : "memory");
     }
     uint32_t ready = 0;
     while (!ready) {
@@ -407,31 +414,43 @@ __device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src
     }
 }
 
+// NEXT kernels: every lane keeps, beside the ray it is traversing, a PREFETCHED next ray in shared memory (origin, 1/d,
+// d, tmax, index; root box already tested), so that a retiring lane restarts with a dozen shared-memory reads instead of
+// waiting for a warp-wide refill (atomic + global load + divides): lanes swap in when a few are idle, and the fetch of the
+// following rays runs off the critical path, many lanes at a time.
+enum : uint32_t { NEXT_OX = 0, NEXT_OY, NEXT_OZ, NEXT_IX, NEXT_IY, NEXT_IZ, NEXT_DX, NEXT_DY, NEXT_DZ, NEXT_TMAX, NEXT_RAY, NEXT_WORDS };
+#define TRQ_SPILL_ENTRIES 16u      // NEXT kernels: stack levels beyond the (at most 16) kept in shared memory live in local memory
+
 // ANY: Scene::hit(any = true). OUT: record format. BLOCK x MINB: CTA size and resident CTAs per SM.
 // TOP: the first P.topCount interior nodes are read from shared memory instead of L1/L2.
-template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP>
+// NEXT: per-lane prefetched next ray + short shared-memory stack (see above).
+template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP, bool NEXT>
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
     extern __shared__ __align__(128) uint32_t smem_u32[];
     __shared__ unsigned long long topBarrier;
     const uint32_t topWords = TOP ? P.topCount * 16u : 0u;
-    const float4* const topNodes = reinterpret_cast<const float4*>(smem_u32);        // [topCount][4]
+    const float4* const topNodes = reinterpret_cast<const float4*>(smem_u32);        // [4][topCount]
     uint32_t* const stk = smem_u32 + topWords + threadIdx.x;                         // [stackDepth][BLOCK]
     uint32_t* const cold = smem_u32 + topWords + P.stackDepth * BLOCK + threadIdx.x; // [COLD_WORDS][BLOCK]
     float* const coldf = reinterpret_cast<float*>(cold);
+    uint32_t* const nxt = cold + COLD_WORDS * BLOCK;                                  // [NEXT_WORDS][BLOCK]   (NEXT kernels)
+    float* const nxtf = reinterpret_cast<float*>(nxt);
     const unsigned lane = threadIdx.x & 31u;
-    constexpr int TAG = ((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT;
+    constexpr int TAG = ((((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0)) * 2 + (NEXT ? 1 : 0);
 
-    if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.nodes, P.topCount * 64u, &topBarrier);
+    if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.topSoA, P.topCount, S.topStride, &topBarrier);
 
     const uint64_t N = live_count(P.n, P.nPtr);
     bool active = false, exhausted = false;
+    bool hasNext = false;                                                            // NEXT kernels
     f3 ro = make_f3(0.f, 0.f, 0.f), rinv = make_f3(0.f, 0.f, 0.f);
     float range_y = 0.0f;
     uint32_t cur = TRQ_REF_DONE_WORD, sp = 0;
+    uint32_t spill[NEXT ? TRQ_SPILL_ENTRIES : 1];
 
-    // A finished ray only retires its lane; its record is finished and written by flush() when the warp next refills,
-    // for all retired lanes at once: the shared-memory reads, the finish-record fetch and the store(s) are then issued
+    // A finished ray only retires its lane; its record is finished and written by flush() when the lane is next given a
+    // ray, for all retired lanes at once: the shared-memory reads, the finish-record fetch and the store(s) are then issued
     // once per refill instead of once per finishing ray (most rays finish alone in their warp step). The lane's
     // registers (ro, range_y) stay untouched between finish() and flush().
     bool pending = false;
@@ -466,27 +485,37 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             pending = false;
         }
     };
+    auto push = [&](uint32_t ref) {
+        if (!NEXT || sp < P.stackDepth) stk[sp * BLOCK] = ref; else spill[sp - P.stackDepth] = ref;
+        ++sp;
+    };
     auto pop = [&]() {
-        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * BLOCK]; }
+        if (sp == 0) cur = TRQ_REF_DONE_WORD;
+        else { --sp; cur = (!NEXT || sp < P.stackDepth) ? stk[sp * BLOCK] : spill[sp - P.stackDepth]; }
+    };
+    // Draws `want` queue slots for the lanes in `mask` (one atomic per warp) and returns this lane's ray index, or ~0.
+    auto draw = [&](unsigned mask) -> uint64_t {
+        const int want = __popc(mask);
+#ifdef TRQ_STATS
+        if (lane == 0) { atomicAdd(&g_stats[4], 1ull); atomicAdd(&g_stats[5], (unsigned long long)want); }
+#endif
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&P.queue->head, (unsigned long long)want);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + (unsigned long long)want >= N) exhausted = true;
+        const uint64_t slot = base + (uint64_t)__popc(mask & ((1u << lane) - 1u));
+        if (!((mask >> lane) & 1u) || slot >= N) return ~0ull;
+        return P.order ? (uint64_t)__ldg(P.order + slot) : slot;
     };
 
     for (;;) {
-        // ---- refill idle lanes from the global queue: one atomic per warp ----
-        const unsigned idleMask = __ballot_sync(0xffffffffu, !active);
-        if (!exhausted && (idleMask == 0xffffffffu || __popc(idleMask) >= (int)P.refillMin)) {
-            const int want = __popc(idleMask);
-#ifdef TRQ_STATS
-            if (lane == 0) { atomicAdd(&g_stats[4], 1ull); atomicAdd(&g_stats[5], (unsigned long long)want); }
-#endif
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&P.queue->head, (unsigned long long)want);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base + (unsigned long long)want >= N) exhausted = true;
-            flush();
-            if (!active) {
-                const uint64_t slot = base + (uint64_t)__popc(idleMask & ((1u << lane) - 1u));
-                if (slot < N) {
-                    const uint64_t idx = P.order ? (uint64_t)__ldg(P.order + slot) : slot;
+        if (!NEXT) {
+            // ---- refill idle lanes from the global queue: one atomic per warp ----
+            const unsigned idleMask = __ballot_sync(0xffffffffu, !active);
+            if (!exhausted && (idleMask == 0xffffffffu || __popc(idleMask) >= (int)P.refillMin)) {
+                const uint64_t idx = draw(idleMask);
+                flush();
+                if (idx != ~0ull) {
                     float4 r0, r1;
                     ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);          // trq_ray is one 32-byte record
                     const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
@@ -509,9 +538,55 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     }
                 }
             }
+        } else {
+            // ---- prefetch: lanes without a next ray draw one (off the critical path, many lanes at a time) ----
+            const unsigned needMask = __ballot_sync(0xffffffffu, !hasNext);
+            const unsigned busyMask = __ballot_sync(0xffffffffu, active || hasNext);
+            if (!exhausted && (__popc(needMask) >= (int)P.refillMin || busyMask == 0u)) {
+                const uint64_t idx = draw(needMask);
+                if (idx != ~0ull) {
+                    float4 r0, r1;
+                    ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);
+                    const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                    const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
+                    const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
+                    if (box_hit(rootMin, rootMax, ray, FLT_MIN, r0.w)) {               // :145
+                        nxtf[NEXT_OX * BLOCK] = ray.o.x; nxtf[NEXT_OY * BLOCK] = ray.o.y; nxtf[NEXT_OZ * BLOCK] = ray.o.z;
+                        nxtf[NEXT_IX * BLOCK] = ray.inv.x; nxtf[NEXT_IY * BLOCK] = ray.inv.y; nxtf[NEXT_IZ * BLOCK] = ray.inv.z;
+                        nxtf[NEXT_DX * BLOCK] = r1.x; nxtf[NEXT_DY * BLOCK] = r1.y; nxtf[NEXT_DZ * BLOCK] = r1.z;
+                        nxtf[NEXT_TMAX * BLOCK] = r0.w;
+                        nxt[NEXT_RAY * BLOCK] = (uint32_t)idx;
+                        hasNext = true;
+                    } else {
+                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                        emit_record<OUT>(P, (uint32_t)idx, z, z);
+                    }
+                }
+            }
+            // ---- swap: idle lanes start their prefetched ray once a few are idle (or nothing else is running) ----
+            const unsigned swapMask = __ballot_sync(0xffffffffu, !active && hasNext);
+            if (swapMask != 0u && (__popc(swapMask) >= (int)P.swapMin || __ballot_sync(0xffffffffu, active) == 0u)) {
+                if (!active && hasNext) {
+                    flush();
+                    ro = make_f3(nxtf[NEXT_OX * BLOCK], nxtf[NEXT_OY * BLOCK], nxtf[NEXT_OZ * BLOCK]);
+                    rinv = make_f3(nxtf[NEXT_IX * BLOCK], nxtf[NEXT_IY * BLOCK], nxtf[NEXT_IZ * BLOCK]);
+                    range_y = nxtf[NEXT_TMAX * BLOCK];
+                    coldf[COLD_TEST_T * BLOCK] = range_y;
+                    cold[COLD_BEST * BLOCK] = 0xffffffffu;
+                    coldf[COLD_U * BLOCK] = 0.0f; coldf[COLD_V * BLOCK] = 0.0f;
+                    cold[COLD_AUX * BLOCK] = 0u;
+                    cold[COLD_RAY * BLOCK] = nxt[NEXT_RAY * BLOCK];
+                    coldf[COLD_DX * BLOCK] = nxtf[NEXT_DX * BLOCK]; coldf[COLD_DY * BLOCK] = nxtf[NEXT_DY * BLOCK]; coldf[COLD_DZ * BLOCK] = nxtf[NEXT_DZ * BLOCK];
+                    sp = 0; cur = S.rootRef; active = true; hasNext = false;
+                }
+                continue;                                             // the swapped-out slots may be refilled before traversing
+            }
         }
         const unsigned actMask = __ballot_sync(0xffffffffu, active);
-        if (actMask == 0u) { if (exhausted) { flush(); break; } else continue; }
+        if (actMask == 0u) {
+            if (exhausted && (!NEXT || __ballot_sync(0xffffffffu, hasNext) == 0u)) { flush(); break; }
+            continue;
+        }
 
         // ---- traverse until enough lanes have retired to make a refill worthwhile ----
         // Two phases per round so that the (rarer) leaf code is not issued on every interior step:
@@ -520,6 +595,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         //     the phase ends when no lane is on an interior node or enough lanes wait at leaves;
         //   leaf phase: every waiting lane tests its primitive and pops.
         const int keepGoing = exhausted ? 0 : (32 - (int)P.refillMin);
+        bool again;
         do {
             for (;;) {
                 const bool onInterior = active && TRQ_REF_KIND(cur) == REF_INTERIOR;
@@ -541,8 +617,8 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                         const uint32_t ni = TRQ_REF_INDEX(cur);
                         float4 q0, q1, q2, q3;
                         if (TOP && ni < P.topCount) {                         // top of the tree: four LDS.128 from this CTA's copy
-                            const float4* tp = topNodes + ni * 4u;
-                            q0 = tp[0]; q1 = tp[1]; q2 = tp[2]; q3 = tp[3];
+                            const float4* tp = topNodes + ni;
+                            q0 = tp[0]; q1 = tp[P.topCount]; q2 = tp[2u * P.topCount]; q3 = tp[3u * P.topCount];
                         } else {
                             const float4* np = S.nodes + (size_t)ni * 4u;
                             ldg8(np, q0, q1);
@@ -556,7 +632,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                             pop();
                         } else {
                             const bool selLeft = tl < tr;                     // :174 (ties -> right, quirk included)
-                            if (lt && rt) { stk[sp * BLOCK] = selLeft ? rref : lref; ++sp; }   // :171-172
+                            if (lt && rt) push(selLeft ? rref : lref);        // :171-172
                             cur = selLeft ? lref : rref;
                         }
                         if (cur == TRQ_REF_DONE_WORD) finish();
@@ -611,7 +687,10 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 else pop();
                 if (cur == TRQ_REF_DONE_WORD) finish();
             }
-        } while (__popc(__ballot_sync(0xffffffffu, active)) > keepGoing);
+            const int nAct = __popc(__ballot_sync(0xffffffffu, active));
+            if (!NEXT) again = nAct > keepGoing;
+            else       again = nAct > 0 && __popc(__ballot_sync(0xffffffffu, !active && hasNext)) < (int)P.swapMin;
+        } while (again);
     }
 
     // ---- epilogue: the last CTA to leave re-arms the queue head for the next launch that draws it and, when a gather
@@ -749,7 +828,7 @@ pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ r
                   const RefVertex* __restrict__ verts, const uint32_t* __restrict__ idx,
                   const RefSphere* __restrict__ spheres, const RefSquare* __restrict__ squares,
                   float4* __restrict__ nodes, float4* __restrict__ tris, float4* __restrict__ sph, float4* __restrict__ sq,
-                  float4* __restrict__ triN) {
+                  float4* __restrict__ triN, float4* __restrict__ topSoA, uint32_t topStride) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nNode) return;
     const uint32_t my = ref[i];
@@ -763,6 +842,10 @@ pack_scene_kernel(const RefBVH* __restrict__ bvh, const uint32_t* __restrict__ r
         out[1] = make_float4(lb.maxi[0], lb.maxi[1], lb.maxi[2], __uint_as_float(ref[r]));
         out[2] = make_float4(rb.mini[0], rb.mini[1], rb.mini[2], 0.0f);
         out[3] = make_float4(rb.maxi[0], rb.maxi[1], rb.maxi[2], 0.0f);
+        if (slot < topStride) {                                 // quarter-major copy of the breadth-first top block (smem staging source)
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) topSoA[(size_t)q * topStride + slot] = out[q];
+        }
     } else if (kind == REF_TRI) {
         const uint32_t p = bvh[i].pIndex;
         const f3 v0 = ld3(verts[idx[3 * p]].v), v1 = ld3(verts[idx[3 * p + 1]].v), v2 = ld3(verts[idx[3 * p + 2]].v);

@@ -62,20 +62,21 @@ constexpr size_t kSmemDynamicMax = kSmemPerBlockMax - 1024u;   // dynamic part: 
 // staged in shared memory. [any][record format] -> kernel.
 struct KernelCfg {
     int block, minb;
-    bool top;
+    bool top, next;
     const void* fn[2][2];
     const char* name;
 };
-#define TRQ_CFG(B, M, T)                                                                                      \
-    { B, M, T,                                                                                                \
-      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T> }, \
-        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T> } }, \
-      #B "x" #M #T }
+#define TRQ_CFG(B, M, T, X)                                                                                   \
+    { B, M, T, X,                                                                                             \
+      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T, X>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T, X> }, \
+        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T, X>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T, X> } }, \
+      #B "x" #M " top=" #T " next=" #X }
 const KernelCfg kCfgs[] = {
-    TRQ_CFG(256, 5, false),       // 0: five CTAs of 256 threads per SM, every node from L1 / L2
-    TRQ_CFG(1024, 1, true),       // 1: one CTA of 1024 threads per SM sharing one staged copy of the top levels
-    TRQ_CFG(512, 2, true),        // 2: two CTAs of 512
-    TRQ_CFG(640, 2, true),        // 3: two CTAs of 640 (1280 threads per SM, as cfg 0)
+    TRQ_CFG(256, 5, false, false),     // 0: five CTAs of 256 threads per SM, every node from L1 / L2, warp-wide refill
+    TRQ_CFG(256, 5, false, true),      // 1: the same with a prefetched next ray per lane and a 16-entry shared-memory stack
+    TRQ_CFG(1024, 1, true, false),     // 2: one CTA of 1024 threads per SM sharing one staged copy of the top levels
+    TRQ_CFG(1024, 1, true, true),      // 3
+    TRQ_CFG(640, 2, true, true),       // 4: two CTAs of 640 (1280 threads per SM, as cfg 0), smaller staged block
 #ifdef TRQ_EXTRA_CFGS
     TRQ_EXTRA_CFGS
 #endif
@@ -104,11 +105,12 @@ struct trq_scene {
     float4* d_sph = nullptr;
     float4* d_sq = nullptr;
     float4* d_triN = nullptr;
+    float4* d_topSoA = nullptr;
     SceneDev dev{};
     uint32_t stackDepth = 1;
     uint32_t maxPIndex = 0;       // largest leaf pIndex (trq_hit16 packs it into 28 bits)
     // per launch configuration: staged top-of-tree nodes, dynamic shared memory, resident CTAs per SM [any][format]
-    struct CfgState { uint32_t topCount = 0; size_t smem = 0; int blocksPerSM[2][2] = {}; bool usable = false; };
+    struct CfgState { uint32_t topCount = 0, stackDepth = 0; size_t smem = 0; int blocksPerSM[2][2] = {}; bool usable = false; };
     CfgState cfg[kNumCfgs];
     int defaultCfg = 0, autoCfg = 0;
     // stream-ordered scratch for TRQ_SORT_RAYS: a private pool that keeps its memory across synchronisations
@@ -138,7 +140,7 @@ void free_scene(trq_scene* s) {
     if (!s) return;
     cudaFree(s->d_spheres); cudaFree(s->d_squares); cudaFree(s->d_cubes);
     cudaFree(s->d_verts); cudaFree(s->d_idx); cudaFree(s->d_bvh);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_sq); cudaFree(s->d_triN);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_sq); cudaFree(s->d_triN); cudaFree(s->d_topSoA);
     cudaFree(s->d_queues);
     if (s->scratchPool) cudaMemPoolDestroy(s->scratchPool);
     for (int b = 0; b < kStageBufs; ++b) {
@@ -329,7 +331,12 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         P.rays = d_rays; P.hits = d_hits; P.n = n;
         // the head is zero: heads are zeroed at creation and every launch's last CTA re-arms the one it used
         P.queue = s->d_queues + (s->queueNext.fetch_add(1) % kQueueRing);
-        P.stackDepth = s->stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
+        static const uint32_t swapMin = [] {
+            const char* e = getenv("TRQ_SWAP_MIN");
+            int v = e ? atoi(e) : 8;
+            return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
+        }();
+        P.stackDepth = cs.stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch; P.swapMin = swapMin;
         P.topCount = K.top ? cs.topCount : 0;
         P.order = nullptr; P.nPtr = nPtr;
         if (gather) {
@@ -551,13 +558,14 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     if (sqBytes && cudaMalloc((void**)&s->d_sq, sqBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(squares %zu B) failed", sqBytes));
     const size_t triNBytes = (size_t)info.nTri * 64;
     if (triNBytes && cudaMalloc((void**)&s->d_triN, triNBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(triangle normals %zu B) failed", triNBytes));
+    if (info.topNodes && cudaMalloc((void**)&s->d_topSoA, (size_t)info.topNodes * 64) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(top-of-tree block) failed"));
     if (cudaMalloc((void**)&s->d_queues, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(queue heads) failed"));
     if (cudaMemset(s->d_queues, 0, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMemset(queue heads) failed"));
 
     {
         const unsigned block = 256, grid = (d->nNode + block - 1) / block;
         pack_scene_kernel<<<grid, block>>>(s->d_bvh, d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres, s->d_squares,
-                                           s->d_nodes, s->d_tris, s->d_sph, s->d_sq, s->d_triN);
+                                           s->d_nodes, s->d_tris, s->d_sph, s->d_sq, s->d_triN, s->d_topSoA, info.topNodes);
         g_launches++;
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "pack_scene_kernel failed: %s", cudaGetErrorString(e)));
@@ -567,6 +575,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     const RefBVH* N = (const RefBVH*)d->bvhList;
     s->dev.spheres = s->d_spheres; s->dev.squares = s->d_squares; s->dev.cubes = s->d_cubes;
     s->dev.verts = s->d_verts; s->dev.idx = s->d_idx; s->dev.bvh = s->d_bvh;
+    s->dev.topSoA = s->d_topSoA; s->dev.topStride = info.topNodes;
     s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.sph = s->d_sph; s->dev.sq = s->d_sq; s->dev.triN = s->d_triN;
     s->dev.rootRef = ref[0];
     for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = N[0].bBOX.mini[k]; s->dev.rootMax[k] = N[0].bBOX.maxi[k]; }
@@ -587,7 +596,10 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     for (int c = 0; c < kNumCfgs; ++c) {
         const KernelCfg& K = kCfgs[c];
         trq_scene::CfgState& cs = s->cfg[c];
-        const size_t perRay = ((size_t)s->stackDepth + COLD_WORDS) * K.block * sizeof(uint32_t);
+        // NEXT kernels keep at most 16 stack levels in shared memory (deeper ones spill to local memory) + the next-ray words
+        cs.stackDepth = K.next ? (s->stackDepth < 16u ? s->stackDepth : 16u) : s->stackDepth;
+        if (K.next && s->stackDepth > cs.stackDepth + TRQ_SPILL_ENTRIES) { cs.usable = false; continue; }
+        const size_t perRay = ((size_t)cs.stackDepth + COLD_WORDS + (K.next ? NEXT_WORDS : 0)) * K.block * sizeof(uint32_t);
         size_t budget = kSmemPerSM / (size_t)K.minb - kSmemBlockReserve;
         if (budget > kSmemDynamicMax) budget = kSmemDynamicMax;
         cs.topCount = 0;
