@@ -1,6 +1,6 @@
 """GPU: every launch configuration of the traversal kernel (CTA size x CTAs per SM; top of the tree staged in shared
-memory by TMA bulk copies or not; warp-wide refill or a prefetched next ray per lane with a 16-entry shared-memory stack
-that spills to local memory) and both record formats (trq_hit, trq_hit16) produce the oracle's results.
+memory by TMA bulk copies or not; the whole far-child stack in shared memory or only its first 8-16 entries with the rest
+spilling to local memory) and both record formats (trq_hit, trq_hit16) produce the oracle's results.
 
 The top-of-tree block is the first `topNodes` packed interior nodes in breadth-first order; a configuration stages a
 prefix of it, so the residency test inside the kernel is "index < topCount" (Render.hh:145-160 re-reads those levels
@@ -24,8 +24,8 @@ def test_every_configuration_matches_the_oracle(built, port):
     torch = _torch()
     from tracer_b200 import Scene, harness as H
     names = Scene.kernel_configs()
-    assert len(names) >= 3 and "top=false next=false" in names[0]
-    assert any("top=true" in n for n in names) and any("next=true" in n for n in names)
+    assert len(names) >= 3 and "top=false sstk=0" in names[0]
+    assert any("top=true" in n for n in names) and any("sstk=8" in n for n in names)
     soup = H.scene_soup(200000, seed=1, extent=0.01)
     mixed = H.scene_reference_cornell()
     cases = [(soup, H.random_rays(300000, seed=2), False), (soup, H.random_rays(100000, seed=3), True),

@@ -261,7 +261,7 @@ struct TraceParams {
     uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
     uint32_t       topCount;       // interior nodes [0, topCount) are staged in shared memory (TOP kernels), else 0
-    uint32_t       swapMin;        // NEXT kernels: idle lanes swap in their prefetched ray when this many are idle
+    uint32_t       l2hint;         // bit 0: ray loads, bit 1: record stores carry an L2 evict_first policy (streamed once)
     uint32_t       pad0;
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
@@ -298,16 +298,38 @@ __device__ __forceinline__ float4 pack_hit16(const float4& o0, const float4& o1)
     return make_float4(o0.x, __uint_as_float(id), o1.x, o1.y);
 }
 
+// Rays are read once and records written once per launch (394 MB per C3 step through a 126 MB L2 that should keep the
+// tree): with an evict_first policy they are the first lines L2 gives up.
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void ldg8_stream(const float4* p, float4& a, float4& b, unsigned long long pol) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void stg8_stream(void* p, const float4& a, const float4& b, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg4_stream(void* p, const float4& a, unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "l"(pol) : "memory");
+}
+
 // One finished record to this rank's buffer and to the same index of every peer's.
 template <int OUT>
-__device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, const float4& o0, const float4& o1) {
+__device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, const float4& o0, const float4& o1, unsigned long long pol) {
     if (OUT == OUT_HIT32) {
-        stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
+        if (P.l2hint & 2u) stg8_stream(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1, pol);
+        else               stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
 #pragma unroll 1
         for (uint32_t p = 0; p < P.nPeer; ++p) stg8(reinterpret_cast<trq_hit*>(P.peerHits[p]) + idx, o0, o1);
     } else {
         const float4 c = pack_hit16(o0, o1);
-        stg4(reinterpret_cast<float4*>(P.hits) + idx, c);
+        if (P.l2hint & 2u) stg4_stream(reinterpret_cast<float4*>(P.hits) + idx, c, pol);
+        else               stg4(reinterpret_cast<float4*>(P.hits) + idx, c);
 #pragma unroll 1
         for (uint32_t p = 0; p < P.nPeer; ++p) stg4(reinterpret_cast<float4*>(P.peerHits[p]) + idx, c);
     }
@@ -414,17 +436,13 @@ __device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src
     }
 }
 
-// NEXT kernels: every lane keeps, beside the ray it is traversing, a PREFETCHED next ray in shared memory (origin, 1/d,
-// d, tmax, index; root box already tested), so that a retiring lane restarts with a dozen shared-memory reads instead of
-// waiting for a warp-wide refill (atomic + global load + divides): lanes swap in when a few are idle, and the fetch of the
-// following rays runs off the critical path, many lanes at a time.
-enum : uint32_t { NEXT_OX = 0, NEXT_OY, NEXT_OZ, NEXT_IX, NEXT_IY, NEXT_IZ, NEXT_DX, NEXT_DY, NEXT_DZ, NEXT_TMAX, NEXT_RAY, NEXT_WORDS };
-#define TRQ_SPILL_ENTRIES 16u      // NEXT kernels: stack levels beyond the (at most 16) kept in shared memory live in local memory
-
 // ANY: Scene::hit(any = true). OUT: record format. BLOCK x MINB: CTA size and resident CTAs per SM.
 // TOP: the first P.topCount interior nodes are read from shared memory instead of L1/L2.
-// NEXT: per-lane prefetched next ray + short shared-memory stack (see above).
-template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP, bool NEXT>
+// SSTK: 0 = the whole far-child stack (scene depth + 1 entries per lane) lives in shared memory; n > 0 = only its first n
+//       entries do and deeper levels spill to a per-thread local-memory array (rarely touched: the stack holds one entry per
+//       ancestor whose BOTH children were hit). A short stack shrinks the CTA's shared memory, and what the carve-out
+//       does not need stays L1 cache.
+template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP, int SSTK>
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
     extern __shared__ __align__(128) uint32_t smem_u32[];
@@ -434,20 +452,18 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     uint32_t* const stk = smem_u32 + topWords + threadIdx.x;                         // [stackDepth][BLOCK]
     uint32_t* const cold = smem_u32 + topWords + P.stackDepth * BLOCK + threadIdx.x; // [COLD_WORDS][BLOCK]
     float* const coldf = reinterpret_cast<float*>(cold);
-    uint32_t* const nxt = cold + COLD_WORDS * BLOCK;                                  // [NEXT_WORDS][BLOCK]   (NEXT kernels)
-    float* const nxtf = reinterpret_cast<float*>(nxt);
     const unsigned lane = threadIdx.x & 31u;
-    constexpr int TAG = ((((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0)) * 2 + (NEXT ? 1 : 0);
+    constexpr int TAG = ((((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0)) * 64 + SSTK;
 
     if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.topSoA, P.topCount, S.topStride, &topBarrier);
 
     const uint64_t N = live_count(P.n, P.nPtr);
+    const unsigned long long l2pol = l2_evict_first_policy();
     bool active = false, exhausted = false;
-    bool hasNext = false;                                                            // NEXT kernels
     f3 ro = make_f3(0.f, 0.f, 0.f), rinv = make_f3(0.f, 0.f, 0.f);
     float range_y = 0.0f;
     uint32_t cur = TRQ_REF_DONE_WORD, sp = 0;
-    uint32_t spill[NEXT ? TRQ_SPILL_ENTRIES : 1];
+    uint32_t spill[SSTK ? 32 - SSTK : 1];                                            // stack entries SSTK.. (trail is 32 bits: depth <= 32)
 
     // A finished ray only retires its lane; its record is finished and written by flush() when the lane is next given a
     // ray, for all retired lanes at once: the shared-memory reads, the finish-record fetch and the store(s) are then issued
@@ -481,17 +497,17 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     o0 = o[0]; o1 = o[1];
                 }
             }
-            emit_record<OUT>(P, cold[COLD_RAY * BLOCK], o0, o1);
+            emit_record<OUT>(P, cold[COLD_RAY * BLOCK], o0, o1, l2pol);
             pending = false;
         }
     };
     auto push = [&](uint32_t ref) {
-        if (!NEXT || sp < P.stackDepth) stk[sp * BLOCK] = ref; else spill[sp - P.stackDepth] = ref;
+        if (SSTK == 0 || sp < (uint32_t)SSTK) stk[sp * BLOCK] = ref; else spill[sp - (uint32_t)SSTK] = ref;
         ++sp;
     };
     auto pop = [&]() {
         if (sp == 0) cur = TRQ_REF_DONE_WORD;
-        else { --sp; cur = (!NEXT || sp < P.stackDepth) ? stk[sp * BLOCK] : spill[sp - P.stackDepth]; }
+        else { --sp; cur = (SSTK == 0 || sp < (uint32_t)SSTK) ? stk[sp * BLOCK] : spill[sp - (uint32_t)SSTK]; }
     };
     // Draws `want` queue slots for the lanes in `mask` (one atomic per warp) and returns this lane's ray index, or ~0.
     auto draw = [&](unsigned mask) -> uint64_t {
@@ -509,84 +525,37 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     };
 
     for (;;) {
-        if (!NEXT) {
-            // ---- refill idle lanes from the global queue: one atomic per warp ----
-            const unsigned idleMask = __ballot_sync(0xffffffffu, !active);
-            if (!exhausted && (idleMask == 0xffffffffu || __popc(idleMask) >= (int)P.refillMin)) {
-                const uint64_t idx = draw(idleMask);
-                flush();
-                if (idx != ~0ull) {
-                    float4 r0, r1;
-                    ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);          // trq_ray is one 32-byte record
-                    const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
-                    ro = ray.o; rinv = ray.inv;
-                    range_y = r0.w;                                        // Render.hh:143  range_t = (FLT_MIN, test_t)
-                    sp = 0;
-                    const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
-                    const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
-                    if (box_hit(rootMin, rootMax, ray, FLT_MIN, range_y)) {            // :145
-                        coldf[COLD_TEST_T * BLOCK] = r0.w;
-                        cold[COLD_BEST * BLOCK] = 0xffffffffu;
-                        coldf[COLD_U * BLOCK] = 0.0f; coldf[COLD_V * BLOCK] = 0.0f;
-                        cold[COLD_AUX * BLOCK] = 0u;
-                        cold[COLD_RAY * BLOCK] = (uint32_t)idx;
-                        coldf[COLD_DX * BLOCK] = r1.x; coldf[COLD_DY * BLOCK] = r1.y; coldf[COLD_DZ * BLOCK] = r1.z;
-                        cur = S.rootRef; active = true;
-                    } else {
-                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                        emit_record<OUT>(P, (uint32_t)idx, z, z);
-                    }
-                }
-            }
-        } else {
-            // ---- prefetch: lanes without a next ray draw one (off the critical path, many lanes at a time) ----
-            const unsigned needMask = __ballot_sync(0xffffffffu, !hasNext);
-            const unsigned busyMask = __ballot_sync(0xffffffffu, active || hasNext);
-            if (!exhausted && (__popc(needMask) >= (int)P.refillMin || busyMask == 0u)) {
-                const uint64_t idx = draw(needMask);
-                if (idx != ~0ull) {
-                    float4 r0, r1;
-                    ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);
-                    const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
-                    const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
-                    const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
-                    if (box_hit(rootMin, rootMax, ray, FLT_MIN, r0.w)) {               // :145
-                        nxtf[NEXT_OX * BLOCK] = ray.o.x; nxtf[NEXT_OY * BLOCK] = ray.o.y; nxtf[NEXT_OZ * BLOCK] = ray.o.z;
-                        nxtf[NEXT_IX * BLOCK] = ray.inv.x; nxtf[NEXT_IY * BLOCK] = ray.inv.y; nxtf[NEXT_IZ * BLOCK] = ray.inv.z;
-                        nxtf[NEXT_DX * BLOCK] = r1.x; nxtf[NEXT_DY * BLOCK] = r1.y; nxtf[NEXT_DZ * BLOCK] = r1.z;
-                        nxtf[NEXT_TMAX * BLOCK] = r0.w;
-                        nxt[NEXT_RAY * BLOCK] = (uint32_t)idx;
-                        hasNext = true;
-                    } else {
-                        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                        emit_record<OUT>(P, (uint32_t)idx, z, z);
-                    }
-                }
-            }
-            // ---- swap: idle lanes start their prefetched ray once a few are idle (or nothing else is running) ----
-            const unsigned swapMask = __ballot_sync(0xffffffffu, !active && hasNext);
-            if (swapMask != 0u && (__popc(swapMask) >= (int)P.swapMin || __ballot_sync(0xffffffffu, active) == 0u)) {
-                if (!active && hasNext) {
-                    flush();
-                    ro = make_f3(nxtf[NEXT_OX * BLOCK], nxtf[NEXT_OY * BLOCK], nxtf[NEXT_OZ * BLOCK]);
-                    rinv = make_f3(nxtf[NEXT_IX * BLOCK], nxtf[NEXT_IY * BLOCK], nxtf[NEXT_IZ * BLOCK]);
-                    range_y = nxtf[NEXT_TMAX * BLOCK];
-                    coldf[COLD_TEST_T * BLOCK] = range_y;
+        // ---- refill idle lanes from the global queue: one atomic per warp ----
+        const unsigned idleMask = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (idleMask == 0xffffffffu || __popc(idleMask) >= (int)P.refillMin)) {
+            const uint64_t idx = draw(idleMask);
+            flush();
+            if (idx != ~0ull) {
+                float4 r0, r1;
+                if (P.l2hint & 1u) ldg8_stream(reinterpret_cast<const float4*>(P.rays + idx), r0, r1, l2pol);
+                else               ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);          // trq_ray is one 32-byte record
+                const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
+                ro = ray.o; rinv = ray.inv;
+                range_y = r0.w;                                        // Render.hh:143  range_t = (FLT_MIN, test_t)
+                sp = 0;
+                const f3 rootMin = make_f3(S.rootMin[0], S.rootMin[1], S.rootMin[2]);
+                const f3 rootMax = make_f3(S.rootMax[0], S.rootMax[1], S.rootMax[2]);
+                if (box_hit(rootMin, rootMax, ray, FLT_MIN, range_y)) {            // :145
+                    coldf[COLD_TEST_T * BLOCK] = r0.w;
                     cold[COLD_BEST * BLOCK] = 0xffffffffu;
                     coldf[COLD_U * BLOCK] = 0.0f; coldf[COLD_V * BLOCK] = 0.0f;
                     cold[COLD_AUX * BLOCK] = 0u;
-                    cold[COLD_RAY * BLOCK] = nxt[NEXT_RAY * BLOCK];
-                    coldf[COLD_DX * BLOCK] = nxtf[NEXT_DX * BLOCK]; coldf[COLD_DY * BLOCK] = nxtf[NEXT_DY * BLOCK]; coldf[COLD_DZ * BLOCK] = nxtf[NEXT_DZ * BLOCK];
-                    sp = 0; cur = S.rootRef; active = true; hasNext = false;
+                    cold[COLD_RAY * BLOCK] = (uint32_t)idx;
+                    coldf[COLD_DX * BLOCK] = r1.x; coldf[COLD_DY * BLOCK] = r1.y; coldf[COLD_DZ * BLOCK] = r1.z;
+                    cur = S.rootRef; active = true;
+                } else {
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    emit_record<OUT>(P, (uint32_t)idx, z, z, l2pol);
                 }
-                continue;                                             // the swapped-out slots may be refilled before traversing
             }
         }
         const unsigned actMask = __ballot_sync(0xffffffffu, active);
-        if (actMask == 0u) {
-            if (exhausted && (!NEXT || __ballot_sync(0xffffffffu, hasNext) == 0u)) { flush(); break; }
-            continue;
-        }
+        if (actMask == 0u) { if (exhausted) { flush(); break; } else continue; }
 
         // ---- traverse until enough lanes have retired to make a refill worthwhile ----
         // Two phases per round so that the (rarer) leaf code is not issued on every interior step:
@@ -595,7 +564,6 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         //     the phase ends when no lane is on an interior node or enough lanes wait at leaves;
         //   leaf phase: every waiting lane tests its primitive and pops.
         const int keepGoing = exhausted ? 0 : (32 - (int)P.refillMin);
-        bool again;
         do {
             for (;;) {
                 const bool onInterior = active && TRQ_REF_KIND(cur) == REF_INTERIOR;
@@ -687,10 +655,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                 else pop();
                 if (cur == TRQ_REF_DONE_WORD) finish();
             }
-            const int nAct = __popc(__ballot_sync(0xffffffffu, active));
-            if (!NEXT) again = nAct > keepGoing;
-            else       again = nAct > 0 && __popc(__ballot_sync(0xffffffffu, !active && hasNext)) < (int)P.swapMin;
-        } while (again);
+        } while (__popc(__ballot_sync(0xffffffffu, active)) > keepGoing);
     }
 
     // ---- epilogue: the last CTA to leave re-arms the queue head for the next launch that draws it and, when a gather
