@@ -261,8 +261,7 @@ struct TraceParams {
     uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
     uint32_t       topCount;       // interior nodes [0, topCount) are staged in shared memory (TOP kernels), else 0
-    uint32_t       l2hint;         // bit 0: ray loads, bit 1: record stores carry an L2 evict_first policy (streamed once)
-    uint32_t       pad0;
+    uint32_t       pad0, pad1;
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
     // Peer fan-out (trq_trace_gather): every finished record is also stored at the same index of nPeer remote buffers
@@ -298,38 +297,16 @@ __device__ __forceinline__ float4 pack_hit16(const float4& o0, const float4& o1)
     return make_float4(o0.x, __uint_as_float(id), o1.x, o1.y);
 }
 
-// Rays are read once and records written once per launch (394 MB per C3 step through a 126 MB L2 that should keep the
-// tree): with an evict_first policy they are the first lines L2 gives up.
-__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void ldg8_stream(const float4* p, float4& a, float4& b, unsigned long long pol) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
-                 : "l"(p), "l"(pol));
-}
-__device__ __forceinline__ void stg8_stream(void* p, const float4& a, const float4& b, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;"
-                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void stg4_stream(void* p, const float4& a, unsigned long long pol) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" :: "l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "l"(pol) : "memory");
-}
-
 // One finished record to this rank's buffer and to the same index of every peer's.
 template <int OUT>
-__device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, const float4& o0, const float4& o1, unsigned long long pol) {
+__device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, const float4& o0, const float4& o1) {
     if (OUT == OUT_HIT32) {
-        if (P.l2hint & 2u) stg8_stream(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1, pol);
-        else               stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
+        stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
 #pragma unroll 1
         for (uint32_t p = 0; p < P.nPeer; ++p) stg8(reinterpret_cast<trq_hit*>(P.peerHits[p]) + idx, o0, o1);
     } else {
         const float4 c = pack_hit16(o0, o1);
-        if (P.l2hint & 2u) stg4_stream(reinterpret_cast<float4*>(P.hits) + idx, c, pol);
-        else               stg4(reinterpret_cast<float4*>(P.hits) + idx, c);
+        stg4(reinterpret_cast<float4*>(P.hits) + idx, c);
 #pragma unroll 1
         for (uint32_t p = 0; p < P.nPeer; ++p) stg4(reinterpret_cast<float4*>(P.peerHits[p]) + idx, c);
     }
@@ -438,11 +415,7 @@ __device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src
 
 // ANY: Scene::hit(any = true). OUT: record format. BLOCK x MINB: CTA size and resident CTAs per SM.
 // TOP: the first P.topCount interior nodes are read from shared memory instead of L1/L2.
-// SSTK: 0 = the whole far-child stack (scene depth + 1 entries per lane) lives in shared memory; n > 0 = only its first n
-//       entries do and deeper levels spill to a per-thread local-memory array (rarely touched: the stack holds one entry per
-//       ancestor whose BOTH children were hit). A short stack shrinks the CTA's shared memory, and what the carve-out
-//       does not need stays L1 cache.
-template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP, int SSTK>
+template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP>
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
     extern __shared__ __align__(128) uint32_t smem_u32[];
@@ -453,17 +426,15 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     uint32_t* const cold = smem_u32 + topWords + P.stackDepth * BLOCK + threadIdx.x; // [COLD_WORDS][BLOCK]
     float* const coldf = reinterpret_cast<float*>(cold);
     const unsigned lane = threadIdx.x & 31u;
-    constexpr int TAG = ((((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0)) * 64 + SSTK;
+    constexpr int TAG = (((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0);
 
     if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.topSoA, P.topCount, S.topStride, &topBarrier);
 
     const uint64_t N = live_count(P.n, P.nPtr);
-    const unsigned long long l2pol = l2_evict_first_policy();
     bool active = false, exhausted = false;
     f3 ro = make_f3(0.f, 0.f, 0.f), rinv = make_f3(0.f, 0.f, 0.f);
     float range_y = 0.0f;
     uint32_t cur = TRQ_REF_DONE_WORD, sp = 0;
-    uint32_t spill[SSTK ? 32 - SSTK : 1];                                            // stack entries SSTK.. (trail is 32 bits: depth <= 32)
 
     // A finished ray only retires its lane; its record is finished and written by flush() when the lane is next given a
     // ray, for all retired lanes at once: the shared-memory reads, the finish-record fetch and the store(s) are then issued
@@ -497,17 +468,13 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     o0 = o[0]; o1 = o[1];
                 }
             }
-            emit_record<OUT>(P, cold[COLD_RAY * BLOCK], o0, o1, l2pol);
+            emit_record<OUT>(P, cold[COLD_RAY * BLOCK], o0, o1);
             pending = false;
         }
     };
-    auto push = [&](uint32_t ref) {
-        if (SSTK == 0 || sp < (uint32_t)SSTK) stk[sp * BLOCK] = ref; else spill[sp - (uint32_t)SSTK] = ref;
-        ++sp;
-    };
+    auto push = [&](uint32_t ref) { stk[sp * BLOCK] = ref; ++sp; };
     auto pop = [&]() {
-        if (sp == 0) cur = TRQ_REF_DONE_WORD;
-        else { --sp; cur = (SSTK == 0 || sp < (uint32_t)SSTK) ? stk[sp * BLOCK] : spill[sp - (uint32_t)SSTK]; }
+        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * BLOCK]; }
     };
     // Draws `want` queue slots for the lanes in `mask` (one atomic per warp) and returns this lane's ray index, or ~0.
     auto draw = [&](unsigned mask) -> uint64_t {
@@ -532,8 +499,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             flush();
             if (idx != ~0ull) {
                 float4 r0, r1;
-                if (P.l2hint & 1u) ldg8_stream(reinterpret_cast<const float4*>(P.rays + idx), r0, r1, l2pol);
-                else               ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);          // trq_ray is one 32-byte record
+                ldg8(reinterpret_cast<const float4*>(P.rays + idx), r0, r1);          // trq_ray is one 32-byte record
                 const RayCtx ray = make_ray_ctx(r0.x, r0.y, r0.z, r1.x, r1.y, r1.z);
                 ro = ray.o; rinv = ray.inv;
                 range_y = r0.w;                                        // Render.hh:143  range_t = (FLT_MIN, test_t)
@@ -550,7 +516,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     cur = S.rootRef; active = true;
                 } else {
                     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    emit_record<OUT>(P, (uint32_t)idx, z, z, l2pol);
+                    emit_record<OUT>(P, (uint32_t)idx, z, z);
                 }
             }
         }

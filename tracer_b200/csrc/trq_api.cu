@@ -63,22 +63,17 @@ constexpr size_t kSmemDynamicMax = kSmemPerBlockMax - 1024u;   // dynamic part: 
 struct KernelCfg {
     int block, minb;
     bool top;
-    int sstk;                 // shared-memory stack entries per lane (0 = scene depth + 1; deeper levels spill to local memory)
     const void* fn[2][2];
     const char* name;
 };
-#define TRQ_CFG(B, M, T, K)                                                                                   \
-    { B, M, T, K,                                                                                             \
-      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T, K>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T, K> }, \
-        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T, K>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T, K> } }, \
-      #B "x" #M " top=" #T " sstk=" #K }
+#define TRQ_CFG(B, M, T)                                                                                      \
+    { B, M, T,                                                                                                \
+      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T> }, \
+        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T> } }, \
+      #B "x" #M " top=" #T }
 const KernelCfg kCfgs[] = {
-    TRQ_CFG(256, 5, false, 0),      // 0: five CTAs of 256 threads per SM, every node from L1 / L2, whole stack in shared memory
-    TRQ_CFG(1024, 1, true, 0),      // 1: one CTA of 1024 threads per SM sharing one staged copy of the top levels
-    TRQ_CFG(256, 5, false, 16),     // 2..4: as 0 with a 16 / 12 / 8-entry shared-memory stack (the rest of the carve-out stays L1)
-    TRQ_CFG(256, 5, false, 12),
-    TRQ_CFG(256, 5, false, 8),
-    TRQ_CFG(256, 6, false, 8),      // 5: six CTAs (40 registers per thread)
+    TRQ_CFG(256, 5, false),       // 0: five CTAs of 256 threads per SM, every node from L1 / L2 (large scenes)
+    TRQ_CFG(1024, 1, true),       // 1: one CTA of 1024 threads per SM sharing one TMA-staged copy of the top levels (small trees)
 #ifdef TRQ_EXTRA_CFGS
     TRQ_EXTRA_CFGS
 #endif
@@ -333,8 +328,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         P.rays = d_rays; P.hits = d_hits; P.n = n;
         // the head is zero: heads are zeroed at creation and every launch's last CTA re-arms the one it used
         P.queue = s->d_queues + (s->queueNext.fetch_add(1) % kQueueRing);
-        static const uint32_t l2hint = [] { const char* e = getenv("TRQ_L2_HINT"); return (uint32_t)(e ? atoi(e) : 0); }();
-        P.stackDepth = cs.stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch; P.l2hint = l2hint;
+        P.stackDepth = cs.stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
         P.topCount = K.top ? cs.topCount : 0;
         P.order = nullptr; P.nPtr = nPtr;
         if (gather) {
@@ -594,8 +588,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     for (int c = 0; c < kNumCfgs; ++c) {
         const KernelCfg& K = kCfgs[c];
         trq_scene::CfgState& cs = s->cfg[c];
-        // short-stack kernels keep K.sstk levels in shared memory; deeper ones spill to local memory (depth <= 32 in all)
-        cs.stackDepth = K.sstk ? (uint32_t)K.sstk : s->stackDepth;
+        cs.stackDepth = s->stackDepth;
         const size_t perRay = ((size_t)cs.stackDepth + COLD_WORDS) * K.block * sizeof(uint32_t);
         size_t budget = kSmemPerSM / (size_t)K.minb - kSmemBlockReserve;
         if (budget > kSmemDynamicMax) budget = kSmemDynamicMax;
@@ -613,14 +606,6 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
         for (int a = 0; a < 2 && e == cudaSuccess; ++a)
             for (int f = 0; f < 2 && e == cudaSuccess; ++f) {
                 if (cs.smem > 48 * 1024) e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDynamicMax);
-                if (e == cudaSuccess) {
-                    // carve out only what MINB resident CTAs need; the rest of the 256 KB stays L1 cache
-                    static const int carveEnv = [] { const char* c_ = getenv("TRQ_CARVEOUT"); return c_ ? atoi(c_) : -1; }();
-                    int pct = (int)(((cs.smem + kSmemBlockReserve) * (size_t)K.minb * 100 + kSmemPerSM - 1) / kSmemPerSM);
-                    if (pct > 100) pct = 100;
-                    if (carveEnv >= 0) pct = carveEnv;
-                    e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-                }
                 if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs.blocksPerSM[a][f], K.fn[a][f], K.block, cs.smem);
                 if (e == cudaSuccess && cs.blocksPerSM[a][f] < 1) cs.usable = false;
             }
@@ -631,7 +616,11 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
         }
     }
     if (!s->cfg[0].usable) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->cfg[0].smem));
+    // Staging the top of the tree pays when the staged block is a large share of the tree (C1 +15 %, C2 +2-3 %) and loses on
+    // 1 M+ triangle scenes (profiles/r02_top_of_tree_experiment.txt): chosen for small trees only.
     s->autoCfg = 0;
+    for (int c = 1; c < kNumCfgs; ++c)
+        if (kCfgs[c].top && s->cfg[c].usable && (uint64_t)info.nInterior <= 16ull * s->cfg[c].topCount) { s->autoCfg = c; break; }
     s->defaultCfg = s->autoCfg;
 
     info.bytesReferenceLayout = (uint64_t)d->nSphere * sizeof(RefSphere) + (uint64_t)d->nSquare * sizeof(RefSquare) +
