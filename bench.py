@@ -161,7 +161,7 @@ class Work:
             s1 = torch.empty(W * Hh, dtype=torch.int32, device=dev); c1 = torch.zeros(1, dtype=torch.int64, device=dev)
             seed_base = rank << 32
             self.launches_per_step = 2
-            self.h0, self.h1 = h0, h1
+            self.h0, self.h1, self.r0, self.r1 = h0, h1, r0, r1
             scene = self.scene
 
             def step():
@@ -198,15 +198,25 @@ class Work:
             self.step = step
 
     def hits(self):
-        """Device hit records of the last step, in the order of self.rays."""
+        """Device hit records of the last step (wavefronts: primary wave, then the bounce wave)."""
         import torch
         if self.path:
             return torch.cat([self.h0, self.h1[:self.n1]])
         return self.d_hits
 
+    def snapshot(self):
+        """(rays, hits) of the LAST step, index-aligned. For the device-resident wavefronts the bounce wave is compacted
+        with one atomic per warp, so its ORDER differs from step to step: rays and hits are read back together."""
+        import torch
+        from tracer_b200 import layout as L
+        if self.path:
+            rays = torch.cat([self.r0, self.r1[:self.n1]]).cpu().numpy().view(L.ray_dtype).reshape(-1)
+            return rays, self.hits()
+        return self.rays, self.d_hits
+
     def close(self):
         self.scene.close()
-        self.d_rays = self.d_hits = self.h0 = self.h1 = None
+        self.d_rays = self.d_hits = self.h0 = self.h1 = self.r0 = self.r1 = None
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -364,9 +374,10 @@ def parity_on(work, idx, nthreads):
     import torch
     from oracle.pyoracle import Port
     from tracer_b200 import layout as L
-    sub = np.ascontiguousarray(work.rays[idx])
+    rays, hits = work.snapshot()
+    sub = np.ascontiguousarray(rays[idx])
     want = Port().trace(work.prim, sub, any=work.any_hit, nthreads=nthreads)["hits"]
-    got = work.hits()[torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(work.device)].cpu().numpy().view(L.hit_dtype).reshape(-1)
+    got = hits[torch.from_numpy(np.asarray(idx, dtype=np.int64)).to(work.device)].cpu().numpy().view(L.hit_dtype).reshape(-1)
     ids_ok = all(np.array_equal(got[k], want[k]) for k in ("flags", "pType", "pIndex", "leafNode"))
     t_ok = np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
     tri = want["pType"] == 3                                  # barycentrics: bit-exact for triangle hits
@@ -637,7 +648,8 @@ def run_gpu_arm(a):
 
     e2e_s = wall(e2e_step, e2e_steps)
     e2e_value = total_rays * e2e_steps / e2e_s / 1e6
-    same = bool(torch.equal(h_hits, d_hits_ref.cpu()))                    # the host path must produce the same bytes as the device path
+    # the host path must produce the same bytes as the device path (wavefronts: the records of that very step)
+    same = bool(torch.equal(h_hits, (work.hits() if path else d_hits_ref).cpu()))
     if not path:
         # the opt-in 16-byte record: half the D2H bytes
         h_hits16 = torch.empty((n, 4), dtype=torch.float32).pin_memory()

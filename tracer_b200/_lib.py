@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtracer_rq.so")
+# TRQ_LIB: developer override (instrumented builds from tools/build_variant.sh); the product library otherwise
+LIB_PATH = os.environ.get("TRQ_LIB") or os.path.join(_HERE, "libtracer_rq.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
