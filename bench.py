@@ -385,9 +385,13 @@ def parity_on(work, idx, nthreads):
     return {"rays": int(sub.size), "ids_bit_exact": bool(ids_ok), "t_bit_exact": bool(t_ok), "barycentrics_bit_exact": bool(uv_ok)}
 
 
-def roofline_of(name, bpr, n, kernel_ms, step_ms, launches_per_step, hbm_peak, peak_src, l2_gbs, traffic):
-    """achieved = algorithmic bytes per launch / kernel time; peak = the ceiling of the level that bounds the workload."""
+def roofline_of(name, bpr, n, kernel_ms, step_ms, launches_per_step, hbm_peak, peak_src, l2_gbs, prof):
+    """achieved = algorithmic bytes per launch / kernel time; peak = the ceiling of the level that bounds the workload.
+    prof: this workload's entry of profiles/traffic.json (ncu --set full capture of the same launch), or None."""
     bound = BOUND[name]
+    traffic = None if not prof else prof.get("traffic_gb")
+    if traffic is not None and prof.get("rays_per_launch") and prof["rays_per_launch"] != n // launches_per_step:
+        traffic = round(traffic * (n / launches_per_step) / prof["rays_per_launch"], 4)     # captured at another shard size: scaled per ray
     achieved = bpr * n / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
     if bound == "l2" and l2_gbs:
         peak, src = l2_gbs, "L2 read bandwidth measured on this GPU in this run (trq_probe_bandwidth: 16-byte loads over a 32 MB set, all SMs); MEASURED_PEAKS.json has no L2 figure"
@@ -403,6 +407,8 @@ def roofline_of(name, bpr, n, kernel_ms, step_ms, launches_per_step, hbm_peak, p
          # what actually crosses the DRAM pins (ncu, per launch) as a fraction of the HBM peak over the kernel's live duration
          "dram_frac": None if (traffic is None or kernel_ms <= 0) else round(traffic * launches_per_step / (kernel_ms * 1e-3) / hbm_peak, 4),
          "l2_read_peak_gbs_measured": None if not l2_gbs else round(l2_gbs, 1)}
+    if prof:      # what ncu says bounds the kernel: the L1 data pipe (one wavefront per divergent 32-byte lane request)
+        r["ncu"] = {k: prof[k] for k in ("l1tex_pct", "lanes_per_inst", "issue_active_pct", "l1_hit_pct", "l2_hit_pct", "dram_pct_of_peak") if k in prof}
     return r
 
 
@@ -649,7 +655,8 @@ def run_gpu_arm(a):
     e2e_s = wall(e2e_step, e2e_steps)
     e2e_value = total_rays * e2e_steps / e2e_s / 1e6
     # the host path must produce the same bytes as the device path (wavefronts: the records of that very step)
-    same = bool(torch.equal(h_hits, (work.hits() if path else d_hits_ref).cpu()))
+    # (compared as bit patterns: sphere uv can be NaN -- asinf just outside [-1, 1] -- and NaN != NaN as floats)
+    same = bool(torch.equal(h_hits.view(torch.int32), (work.hits() if path else d_hits_ref).cpu().view(torch.int32)))
     if not path:
         # the opt-in 16-byte record: half the D2H bytes
         h_hits16 = torch.empty((n, 4), dtype=torch.float32).pin_memory()
@@ -674,7 +681,7 @@ def run_gpu_arm(a):
         pipe_s = D.max_over_ranks(time.perf_counter() - t)
         e2e_extra["e2e_pipelined"] = {"value": round(total_rays * e2e_steps / pipe_s / 1e6, 2), "unit": UNIT, "steps": e2e_steps,
                                       "note": "K TRQ_HOST_ASYNC calls queued back to back + one trq_host_sync; same bytes per step as e2e",
-                                      "equals_device_path": bool(torch.equal(h_hits2, d_hits_ref.cpu()))}
+                                      "equals_device_path": bool(torch.equal(h_hits2.view(torch.int32), d_hits_ref.cpu().view(torch.int32)))}
         del h_hits2, h_hits16
     del h_hits
 

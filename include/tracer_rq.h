@@ -151,6 +151,19 @@ int  trq_device_count(void);
 /* Uploads the six arrays to `device`, validates the tree (indices in range, 2N-1 nodes
  * reachable, depth <= 32) and derives the packed traversal layout on the device. */
 int  trq_scene_create(const trq_scene_desc* desc, int device, trq_scene** out);
+/* The same for a scene that already lives on the GPU: every array of `desc` is a DEVICE pointer on `device` (for
+ * example bvhList from trq_bvh_build_tree_device). The arrays are copied device to device; validation and numbering
+ * run as kernels, so no array crosses PCIe (128 bytes of counters come back). Same checks and same packed layout as
+ * trq_scene_create, with one difference: EVERY node of bvhList must be reachable from the root. */
+int  trq_scene_create_device(const trq_scene_desc* desc, int device, trq_scene** out);
+
+/* Refit after the vertices moved (animated meshes): same topology, new boxes. Triangle leaf boxes are recomputed from
+ * the new vertices (min / max of the three, AAPLRenderer.mm:575-589), interior boxes bottom-up as the union of their
+ * children (AABB::make, BVH.hh:229-231), the packed layout is derived again; all on the device. triList holds the
+ * scene's nVert vertices: a device pointer, or a host pointer with TRQ_HOST_PTRS. Synchronous: waits for traces in
+ * flight, returns when the scene is ready for the next trq_trace. */
+int  trq_scene_update_vertices(trq_scene* scene, const void* triList, uint32_t nVert, uint32_t flags);
+
 int  trq_scene_destroy(trq_scene* scene);
 int  trq_scene_info(const trq_scene* scene, trq_scene_info_t* info);
 
@@ -302,6 +315,10 @@ int  trq_bvh_build_tree(void* bvhList, uint32_t nLeaves, uint32_t* nNodeOut, uin
  * primitives share one centroid (the reference then falls back to std::sort, whose order of equal keys is
  * unspecified). TRQ_ERR_NO_DEVICE without a GPU (use the host builder). */
 int  trq_bvh_build_tree_gpu(void* bvhList, uint32_t nLeaves, int device, uint32_t* nNodeOut, uint32_t* maxDepthOut);
+
+/* The same build with the array in DEVICE memory on `device` (leaves in d_bvhList[0..nLeaves), capacity 2*nLeaves-1
+ * nodes; the result replaces them): build -> trq_scene_create_device without the tree ever visiting the host. */
+int  trq_bvh_build_tree_device(void* d_bvhList, uint32_t nLeaves, int device, uint32_t* nNodeOut, uint32_t* maxDepthOut);
 
 #ifdef __cplusplus
 }

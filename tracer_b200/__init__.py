@@ -7,6 +7,6 @@ Public surface (host mirror of the reference interface, over the C-ABI in includ
     multi-GPU sharding helpers            tracer_b200.dist
 """
 from . import layout
-from .scene import BVHBuilder, MultiGpuScene, Primitive, Scene, hits_to_numpy, launch_count, probe_bandwidth, rays_to_torch
+from .scene import BVHBuilder, DevicePrimitive, MultiGpuScene, Primitive, Scene, hits_to_numpy, launch_count, probe_bandwidth, rays_to_torch
 
-__all__ = ["layout", "Primitive", "Scene", "MultiGpuScene", "BVHBuilder", "hits_to_numpy", "rays_to_torch", "launch_count", "probe_bandwidth"]
+__all__ = ["layout", "Primitive", "DevicePrimitive", "Scene", "MultiGpuScene", "BVHBuilder", "hits_to_numpy", "rays_to_torch", "launch_count", "probe_bandwidth"]

@@ -341,7 +341,7 @@ swap_kernel(const uint32_t* __restrict__ seg, uint32_t n, const BNode* __restric
 __global__ void __launch_bounds__(128)
 emit_kernel(BNode* nodes, uint32_t nNodes, const uint32_t* __restrict__ idx, const float4* __restrict__ cen,
             RefBVH* out /* final layout: root at 0, pre-shift index j at j+1 */, uint32_t nLeaves,
-            BNode* next, uint32_t* nNext, uint32_t* maxDepth, uint32_t depth) {
+            BNode* next, uint32_t cap /* entries of `next` */, uint32_t* nNext, uint32_t* overflow, uint32_t* maxDepth, uint32_t depth) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nNodes) return;
     BNode& nd = nodes[i];
@@ -366,13 +366,13 @@ emit_kernel(BNode* nodes, uint32_t nNodes, const uint32_t* __restrict__ idx, con
         childPre[1] = rspan == 1 ? idx[nd.mid] : nLeaves + rbase + rspan - 2;
         if (lspan > 1) {
             const uint32_t slot = atomicAdd(nNext, 1u);
-            next[slot].start = nd.start; next[slot].end = nd.mid; next[slot].base = lbase;
-            nd.child[0] = slot;
+            if (slot < cap) { next[slot].start = nd.start; next[slot].end = nd.mid; next[slot].base = lbase; nd.child[0] = slot; }
+            else atomicExch(overflow, 1u);                          // cannot happen (a level has at most n/2 open subtrees); never write past the table
         }
         if (rspan > 1) {
             const uint32_t slot = atomicAdd(nNext, 1u);
-            next[slot].start = nd.mid; next[slot].end = nd.end; next[slot].base = rbase;
-            nd.child[1] = slot;
+            if (slot < cap) { next[slot].start = nd.mid; next[slot].end = nd.end; next[slot].base = rbase; nd.child[1] = slot; }
+            else atomicExch(overflow, 1u);
         }
         atomicMax(maxDepth, depth);
     }

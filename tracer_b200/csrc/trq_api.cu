@@ -19,6 +19,8 @@
 #include "../../include/tracer_rq.h"
 #include "host/error.h"
 #include "host/layout.h"
+#include "host/scratch.h"
+#include "kernels/plan_scene.cuh"
 #include "kernels/trace_kernels.cuh"
 
 using namespace trq;
@@ -30,6 +32,8 @@ std::atomic<uint64_t> g_launches{0};
 }  // namespace
 
 namespace trq { void note_launches(uint64_t n) { g_launches += n; } }   // other translation units (GPU builder)
+
+
 
 namespace {
 
@@ -103,6 +107,8 @@ struct trq_scene {
     float4* d_sq = nullptr;
     float4* d_triN = nullptr;
     float4* d_topSoA = nullptr;
+    uint32_t* d_ref = nullptr;    // packed reference of every bvhList node (kept for refits)
+    uint32_t nNode = 0, nVert = 0, topStride = 0;
     SceneDev dev{};
     uint32_t stackDepth = 1;
     uint32_t maxPIndex = 0;       // largest leaf pIndex (trq_hit16 packs it into 28 bits)
@@ -121,7 +127,10 @@ struct trq_scene {
     uint64_t stageCap = 0;
     trq_ray* d_stageRays[kStageBufs] = {};
     trq_hit* d_stageHits[kStageBufs] = {};
-    cudaStream_t stageStream[kStageBufs] = {};   // one stream per staging buffer: copy in, trace, copy out in stream order
+    cudaStream_t stageStream[kStageBufs] = {};   // one compute stream per staging buffer (the tails of consecutive chunk kernels overlap)
+    cudaStream_t stageIn = nullptr, stageOut = nullptr;   // ALL H2D copies on one stream, all D2H copies on another: each copy
+                                                          // engine runs its copies back to back at full link rate
+    cudaEvent_t evIn[kStageBufs] = {}, evTraced[kStageBufs] = {}, evOut[kStageBufs] = {};
     bool stageReady = false;
     uint64_t stageSeq = 0;        // chunks ever staged (ring position)
     // optional per-kernel timing (trq_profile_enable): events around the trace and resolve kernels
@@ -137,13 +146,18 @@ void free_scene(trq_scene* s) {
     if (!s) return;
     cudaFree(s->d_spheres); cudaFree(s->d_squares); cudaFree(s->d_cubes);
     cudaFree(s->d_verts); cudaFree(s->d_idx); cudaFree(s->d_bvh);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_sq); cudaFree(s->d_triN); cudaFree(s->d_topSoA);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_sq); cudaFree(s->d_triN); cudaFree(s->d_topSoA); cudaFree(s->d_ref);
     cudaFree(s->d_queues);
     if (s->scratchPool) cudaMemPoolDestroy(s->scratchPool);
     for (int b = 0; b < kStageBufs; ++b) {
         cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
         if (s->stageStream[b]) cudaStreamDestroy(s->stageStream[b]);
+        if (s->evIn[b]) cudaEventDestroy(s->evIn[b]);
+        if (s->evTraced[b]) cudaEventDestroy(s->evTraced[b]);
+        if (s->evOut[b]) cudaEventDestroy(s->evOut[b]);
     }
+    if (s->stageIn) cudaStreamDestroy(s->stageIn);
+    if (s->stageOut) cudaStreamDestroy(s->stageOut);
     for (int k = 0; k < kProfRing; ++k)
         for (int j = 0; j < 3; ++j) if (s->evProf[k][j]) cudaEventDestroy(s->evProf[k][j]);
     delete s;
@@ -389,14 +403,23 @@ void timeline_dump() {
 #endif
 
 int sync_staging(trq_scene* s) {
+    if (s->stageOut) TRQ_CUDA(cudaStreamSynchronize(s->stageOut));   // the last D2H of every chunk: everything before it is done
     for (int b = 0; b < kStageBufs; ++b)
         if (s->stageStream[b]) TRQ_CUDA(cudaStreamSynchronize(s->stageStream[b]));
+    if (s->stageIn) TRQ_CUDA(cudaStreamSynchronize(s->stageIn));
     return TRQ_OK;
 }
 
 int ensure_staging(trq_scene* s, uint64_t chunk) {
     if (!s->stageReady) {
-        for (int b = 0; b < kStageBufs; ++b) TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageStream[b], cudaStreamNonBlocking));
+        TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageIn, cudaStreamNonBlocking));
+        TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageOut, cudaStreamNonBlocking));
+        for (int b = 0; b < kStageBufs; ++b) {
+            TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageStream[b], cudaStreamNonBlocking));
+            TRQ_CUDA(cudaEventCreateWithFlags(&s->evIn[b], cudaEventDisableTiming));
+            TRQ_CUDA(cudaEventCreateWithFlags(&s->evTraced[b], cudaEventDisableTiming));
+            TRQ_CUDA(cudaEventCreateWithFlags(&s->evOut[b], cudaEventDisableTiming));
+        }
         s->stageReady = true;
     }
     if (chunk > s->stageCap) {
@@ -416,9 +439,14 @@ int ensure_staging(trq_scene* s, uint64_t chunk) {
     return TRQ_OK;
 }
 
-// Host-pointer path: the batch is cut into chunks; chunk k goes through staging buffer k % kStageBufs on that
-// buffer's own stream (copy in, trace, copy out, in stream order). Different chunks overlap on the two copy engines
-// and the SMs, buffer reuse is ordered by the stream itself, and a chunk costs four driver calls.
+// Host-pointer path: the batch is cut into chunks; chunk k uses staging buffer b = k % kStageBufs. Three stages,
+// chained by events per buffer:
+//   copy-in stream   H2D of the rays (after the kernel that last read this buffer)            -> evIn[b]
+//   stream of b      the trace (after evIn[b] and after the D2H that last read this buffer)   -> evTraced[b]
+//   copy-out stream  D2H of the records (after evTraced[b])                                   -> evOut[b]
+// Every H2D copy is on ONE stream and every D2H copy on another, so each copy engine runs its copies back to back at the
+// full link rate (with one stream per chunk, the H2D copies of 2-3 chunks shared the link and finished late: 41 GB/s
+// instead of 48.5 GB/s, profiles/r02_e2e_timeline_before.txt); kernels of consecutive chunks overlap their tails.
 // A synchronous call pays one chunk of H2D before anything overlaps and one chunk of trace + D2H after the last copy
 // in; the chunk sizes therefore ramp up at the front and down at the back (1/8, 1/4, 1/2, 1, ..., 1, 1/2, 1/4, 1/8).
 int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, void* hits) {
@@ -451,20 +479,27 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, vo
         const int b = (int)(s->stageSeq++ % kStageBufs);       // runs across calls: TRQ_HOST_ASYNC calls share the ring
         cudaStream_t st = s->stageStream[b];
 #ifdef TRQ_STAGE_TIMELINE
-        cudaEvent_t* tl = timeline_events(4); cudaEventRecord(tl[0], st);
+        cudaEvent_t* tl = timeline_events(4); cudaEventRecord(tl[0], s->stageIn);
 #endif
-        TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, st));
+        TRQ_CUDA(cudaStreamWaitEvent(s->stageIn, s->evTraced[b], 0));          // the kernel that last read these staged rays
+        TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, s->stageIn));
+        TRQ_CUDA(cudaEventRecord(s->evIn[b], s->stageIn));
 #ifdef TRQ_STAGE_TIMELINE
-        cudaEventRecord(tl[1], st);
+        cudaEventRecord(tl[1], s->stageIn);
 #endif
+        TRQ_CUDA(cudaStreamWaitEvent(st, s->evIn[b], 0));
+        TRQ_CUDA(cudaStreamWaitEvent(st, s->evOut[b], 0));                     // the D2H that last read these staged records
         rc = launch_trace(s, s->d_stageRays[b], m, flags, s->d_stageHits[b], st);
         if (rc != TRQ_OK) return rc;
+        TRQ_CUDA(cudaEventRecord(s->evTraced[b], st));
 #ifdef TRQ_STAGE_TIMELINE
         cudaEventRecord(tl[2], st);
 #endif
-        TRQ_CUDA(cudaMemcpyAsync((uint8_t*)hits + done * recBytes, s->d_stageHits[b], m * recBytes, cudaMemcpyDeviceToHost, st));
+        TRQ_CUDA(cudaStreamWaitEvent(s->stageOut, s->evTraced[b], 0));
+        TRQ_CUDA(cudaMemcpyAsync((uint8_t*)hits + done * recBytes, s->d_stageHits[b], m * recBytes, cudaMemcpyDeviceToHost, s->stageOut));
+        TRQ_CUDA(cudaEventRecord(s->evOut[b], s->stageOut));
 #ifdef TRQ_STAGE_TIMELINE
-        cudaEventRecord(tl[3], st);
+        cudaEventRecord(tl[3], s->stageOut);
 #endif
         done += m;
     }
@@ -498,79 +533,63 @@ void trq_debug_stats(unsigned long long* out, int reset) {
 }
 #endif
 
-int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
-    if (!d || !out) return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: NULL argument");
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+int upload_from(T** dst, const void* src, size_t count, cudaMemcpyKind kind) {
+    *dst = nullptr;
+    if (count == 0) return TRQ_OK;
+    TRQ_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    TRQ_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), kind));
+    return TRQ_OK;
+}
+
+int check_desc(const trq_scene_desc* d, trq_scene** out, const char* who) {
+    if (!d || !out) return trq::fail(TRQ_ERR_INVALID, "%s: NULL argument", who);
     *out = nullptr;
-    if (!d->bvhList || d->nNode == 0) return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: empty bvhList");
+    if (!d->bvhList || d->nNode == 0) return trq::fail(TRQ_ERR_INVALID, "%s: empty bvhList", who);
     if ((d->nSphere && !d->sphereList) || (d->nSquare && !d->squareList) || (d->nCube && !d->cubeList) ||
         (d->nVert && !d->triList) || (d->nTri && !d->idxList))
-        return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: NULL array with non-zero count");
+        return trq::fail(TRQ_ERR_INVALID, "%s: NULL array with non-zero count", who);
+    return TRQ_OK;
+}
 
-    trq_scene_info_t info{};
-    std::vector<uint32_t> ref;
-    uint32_t maxPIndex = 0;
-    int rc = plan_layout(d, ref, info, maxPIndex);             // pure host validation: runs without a GPU
-    if (rc != TRQ_OK) return rc;
-
-    int ndev = trq_device_count();
-    if (ndev <= 0) return trq::fail(TRQ_ERR_NO_DEVICE, "trq_scene_create: no CUDA device (there is no CPU fallback)");
-    if (device < 0 || device >= ndev) return trq::fail(TRQ_ERR_INVALID, "trq_scene_create: device %d out of range (%d devices)", device, ndev);
-
-    DeviceGuard guard(device);
-    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-
-    trq_scene* s = new (std::nothrow) trq_scene();
-    if (!s) return trq::fail(TRQ_ERR_NOMEM, "trq_scene_create: out of host memory");
-    s->device = device;
-    s->maxPIndex = maxPIndex;
-    auto bail = [&](int code) { free_scene(s); return code; };
-
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaGetDeviceProperties failed"));
-    s->numSMs = prop.multiProcessorCount;
-
-    if ((rc = upload(&s->d_spheres, d->sphereList, d->nSphere)) != TRQ_OK) return bail(rc);
-    if ((rc = upload(&s->d_squares, d->squareList, d->nSquare)) != TRQ_OK) return bail(rc);
-    if ((rc = upload(&s->d_cubes, d->cubeList, d->nCube)) != TRQ_OK) return bail(rc);
-    if ((rc = upload(&s->d_verts, d->triList, d->nVert)) != TRQ_OK) return bail(rc);
-    if ((rc = upload(&s->d_idx, d->idxList, (size_t)d->nTri * 3)) != TRQ_OK) return bail(rc);
-    if ((rc = upload(&s->d_bvh, d->bvhList, d->nNode)) != TRQ_OK) return bail(rc);
-
-    uint32_t* d_ref = nullptr;
-    if ((rc = upload(&d_ref, ref.data(), ref.size())) != TRQ_OK) return bail(rc);
-    auto bail2 = [&](int code) { cudaFree(d_ref); return bail(code); };
-
+// The part of scene creation that is the same for host and device input: the six reference arrays are resident
+// (s->d_*), every node has its packed reference in s->d_ref, `info` holds the counts. Allocates and derives the packed
+// layout on the device and sizes the launch configurations.
+int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, uint32_t nSqLeaf, uint32_t rootRef,
+                 const float rootMin[3], const float rootMax[3]) {
+    const int device = s->device;
     const size_t nodeBytes = (size_t)info.nInterior * 64, triBytes = (size_t)info.nTri * 16 * TRQ_TRI_STRIDE, sphBytes = (size_t)info.nSphere * 32;
-    uint32_t nSqLeaf = 0;
-    for (uint32_t r : ref) if (r != TRQ_REF_DONE_WORD && TRQ_REF_KIND(r) == REF_SQUARE) ++nSqLeaf;
     const size_t sqBytes = (size_t)nSqLeaf * 16 * TRQ_SQ_STRIDE;
-    if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes));
-    if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes));
-    if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes));
-    if (sqBytes && cudaMalloc((void**)&s->d_sq, sqBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(squares %zu B) failed", sqBytes));
+    if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes);
+    if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes);
+    if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes);
+    if (sqBytes && cudaMalloc((void**)&s->d_sq, sqBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(squares %zu B) failed", sqBytes);
     const size_t triNBytes = (size_t)info.nTri * 64;
-    if (triNBytes && cudaMalloc((void**)&s->d_triN, triNBytes) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(triangle normals %zu B) failed", triNBytes));
-    if (info.topNodes && cudaMalloc((void**)&s->d_topSoA, (size_t)info.topNodes * 64) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(top-of-tree block) failed"));
-    if (cudaMalloc((void**)&s->d_queues, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(queue heads) failed"));
-    if (cudaMemset(s->d_queues, 0, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "cudaMemset(queue heads) failed"));
+    if (triNBytes && cudaMalloc((void**)&s->d_triN, triNBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(triangle normals %zu B) failed", triNBytes);
+    if (info.topNodes && cudaMalloc((void**)&s->d_topSoA, (size_t)info.topNodes * 64) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(top-of-tree block) failed");
+    if (cudaMalloc((void**)&s->d_queues, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(queue heads) failed");
+    if (cudaMemset(s->d_queues, 0, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMemset(queue heads) failed");
 
+    s->nNode = d->nNode; s->nVert = d->nVert; s->topStride = info.topNodes;
     {
         const unsigned block = 256, grid = (d->nNode + block - 1) / block;
-        pack_scene_kernel<<<grid, block>>>(s->d_bvh, d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres, s->d_squares,
+        pack_scene_kernel<<<grid, block>>>(s->d_bvh, s->d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres, s->d_squares,
                                            s->d_nodes, s->d_tris, s->d_sph, s->d_sq, s->d_triN, s->d_topSoA, info.topNodes);
         g_launches++;
         cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) return bail2(trq::fail(TRQ_ERR_CUDA, "pack_scene_kernel failed: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "pack_scene_kernel failed: %s", cudaGetErrorString(e));
     }
-    cudaFree(d_ref);
 
-    const RefBVH* N = (const RefBVH*)d->bvhList;
     s->dev.spheres = s->d_spheres; s->dev.squares = s->d_squares; s->dev.cubes = s->d_cubes;
     s->dev.verts = s->d_verts; s->dev.idx = s->d_idx; s->dev.bvh = s->d_bvh;
     s->dev.topSoA = s->d_topSoA; s->dev.topStride = info.topNodes;
     s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.sph = s->d_sph; s->dev.sq = s->d_sq; s->dev.triN = s->d_triN;
-    s->dev.rootRef = ref[0];
-    for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = N[0].bBOX.mini[k]; s->dev.rootMax[k] = N[0].bBOX.maxi[k]; }
+    s->dev.rootRef = rootRef;
+    for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = rootMin[k]; s->dev.rootMax[k] = rootMax[k]; }
     s->dev.nNode = d->nNode;
     s->stackDepth = info.maxDepth + 1;
     {
@@ -582,7 +601,7 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
         cudaError_t e = cudaMemPoolCreate(&s->scratchPool, &pp);
         unsigned long long keep = ~0ull;
         if (e == cudaSuccess) e = cudaMemPoolSetAttribute(s->scratchPool, cudaMemPoolAttrReleaseThreshold, &keep);
-        if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(e)));
+        if (e != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(e));
     }
     // launch configurations: per-CTA shared memory = staged top-of-tree nodes + far-child stack + cold per-ray words
     for (int c = 0; c < kNumCfgs; ++c) {
@@ -610,12 +629,12 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
                 if (e == cudaSuccess && cs.blocksPerSM[a][f] < 1) cs.usable = false;
             }
         if (e != cudaSuccess) {
-            if (c == 0) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel (%s) occupancy query failed: %s", K.name, cudaGetErrorString(e)));
+            if (c == 0) return trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel (%s) occupancy query failed: %s", K.name, cudaGetErrorString(e));
             cudaGetLastError();                                // an optional configuration that does not fit: not offered
             cs.usable = false;
         }
     }
-    if (!s->cfg[0].usable) return bail(trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->cfg[0].smem));
+    if (!s->cfg[0].usable) return trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->cfg[0].smem);
     // Staging the top of the tree pays when the staged block is a large share of the tree (C1 +15 %, C2 +2-3 %) and loses on
     // 1 M+ triangle scenes (profiles/r02_top_of_tree_experiment.txt): chosen for small trees only.
     s->autoCfg = 0;
@@ -629,7 +648,157 @@ int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
     info.bytesPacked = nodeBytes + triBytes + sphBytes + sqBytes + triNBytes;
     info.device = device;
     s->info = info;
+    return TRQ_OK;
+}
+
+int open_scene(int device, trq_scene** sOut, const char* who) {
+    int ndev = trq_device_count();
+    if (ndev <= 0) return trq::fail(TRQ_ERR_NO_DEVICE, "%s: no CUDA device (there is no CPU fallback)", who);
+    if (device < 0 || device >= ndev) return trq::fail(TRQ_ERR_INVALID, "%s: device %d out of range (%d devices)", who, device, ndev);
+    trq_scene* s = new (std::nothrow) trq_scene();
+    if (!s) return trq::fail(TRQ_ERR_NOMEM, "%s: out of host memory", who);
+    s->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return trq::fail(TRQ_ERR_CUDA, "cudaGetDeviceProperties failed"); }
+    s->numSMs = prop.multiProcessorCount;
+    *sOut = s;
+    return TRQ_OK;
+}
+
+const char* plan_error_text(uint32_t code) {
+    switch (code) {
+        case plan::ERR_CHILD_RANGE: return "child index out of range";
+        case plan::ERR_CHILDREN:    return "interior node has invalid children";
+        case plan::ERR_PARENT_LINK: return "parent / child links do not agree (not a tree)";
+        case plan::ERR_ROOT_PARENT: return "the root's parent must be 0 (BVH.hh:264)";
+        case plan::ERR_LEAF_INDEX:  return "leaf pIndex out of range";
+        case plan::ERR_VERTEX_INDEX: return "triangle vertex index out of range";
+        case plan::ERR_DEPTH:       return "interior depth exceeds the 32-bit trail (Render.hh:140)";
+        case plan::ERR_UNREACHABLE: return "nodes not reachable from the root";
+        default: return "unknown";
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int trq_scene_create(const trq_scene_desc* d, int device, trq_scene** out) {
+    int rc = check_desc(d, out, "trq_scene_create");
+    if (rc != TRQ_OK) return rc;
+
+    trq_scene_info_t info{};
+    std::vector<uint32_t> ref;
+    uint32_t maxPIndex = 0;
+    rc = plan_layout(d, ref, info, maxPIndex);                 // pure host validation: runs without a GPU
+    if (rc != TRQ_OK) return rc;
+
+    trq_scene* s = nullptr;
+    if ((rc = open_scene(device, &s, "trq_scene_create")) != TRQ_OK) return rc;
+    DeviceGuard guard(device);
+    auto bail = [&](int code) { free_scene(s); return code; };
+    if (!guard.ok) return bail(trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+    s->maxPIndex = maxPIndex;
+
+    if ((rc = upload(&s->d_spheres, d->sphereList, d->nSphere)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_squares, d->squareList, d->nSquare)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_cubes, d->cubeList, d->nCube)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_verts, d->triList, d->nVert)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_idx, d->idxList, (size_t)d->nTri * 3)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_bvh, d->bvhList, d->nNode)) != TRQ_OK) return bail(rc);
+    if ((rc = upload(&s->d_ref, ref.data(), ref.size())) != TRQ_OK) return bail(rc);
+
+    uint32_t nSqLeaf = 0;
+    for (uint32_t r : ref) if (r != TRQ_REF_DONE_WORD && TRQ_REF_KIND(r) == REF_SQUARE) ++nSqLeaf;
+    const RefBVH* N = (const RefBVH*)d->bvhList;
+    if ((rc = finish_scene(s, d, info, nSqLeaf, ref[0], N[0].bBOX.mini, N[0].bBOX.maxi)) != TRQ_OK) return bail(rc);
     *out = s;
+    return TRQ_OK;
+}
+
+// Device-resident input: the six arrays are DEVICE pointers on `device` (e.g. the node array trq_bvh_build_tree_device
+// just produced). They are copied device to device, and validation + numbering run as kernels (kernels/plan_scene.cuh):
+// no array crosses PCIe, 128 bytes of counters come back.
+int trq_scene_create_device(const trq_scene_desc* d, int device, trq_scene** out) {
+    int rc = check_desc(d, out, "trq_scene_create_device");
+    if (rc != TRQ_OK) return rc;
+    trq_scene* s = nullptr;
+    if ((rc = open_scene(device, &s, "trq_scene_create_device")) != TRQ_OK) return rc;
+    DeviceGuard guard(device);
+    auto bail = [&](int code) { free_scene(s); return code; };
+    if (!guard.ok) return bail(trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+    if ((rc = upload_from(&s->d_spheres, d->sphereList, d->nSphere, k)) != TRQ_OK) return bail(rc);
+    if ((rc = upload_from(&s->d_squares, d->squareList, d->nSquare, k)) != TRQ_OK) return bail(rc);
+    if ((rc = upload_from(&s->d_cubes, d->cubeList, d->nCube, k)) != TRQ_OK) return bail(rc);
+    if ((rc = upload_from(&s->d_verts, d->triList, d->nVert, k)) != TRQ_OK) return bail(rc);
+    if ((rc = upload_from(&s->d_idx, d->idxList, (size_t)d->nTri * 3, k)) != TRQ_OK) return bail(rc);
+    if ((rc = upload_from(&s->d_bvh, d->bvhList, d->nNode, k)) != TRQ_OK) return bail(rc);
+    const uint32_t n = d->nNode;
+    if (cudaMalloc((void**)&s->d_ref, (size_t)n * sizeof(uint32_t)) != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(refs) failed"));
+
+    plan::PlanInfo hostInfo;
+    {
+        trq::PoolScratch mem(device, nullptr);
+        plan::Counts* cnt; uint32_t *leafTotal, *arrivals, *pre, *topPos, *sortedPre; plan::PlanInfo* dInfo;
+        if (!(mem.alloc(&cnt, n) && mem.alloc(&leafTotal, n) && mem.alloc(&arrivals, n) && mem.alloc(&pre, n) && mem.alloc(&topPos, n) &&
+              mem.alloc(&sortedPre, 2048) && mem.alloc(&dInfo, 1)))
+            return bail(trq::fail(TRQ_ERR_NOMEM, "trq_scene_create_device: out of device memory"));
+        cudaMemsetAsync(arrivals, 0, (size_t)n * 4); cudaMemsetAsync(topPos, 0, (size_t)n * 4);
+        cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(plan::Counts)); cudaMemsetAsync(leafTotal, 0, (size_t)n * 4);
+        cudaMemsetAsync(dInfo, 0, sizeof(plan::PlanInfo)); cudaMemsetAsync(s->d_ref, 0xff, (size_t)n * 4);
+        const unsigned grid = (n + 255) / 256;
+        plan::validate_kernel<<<grid, 256>>>(s->d_bvh, n, d->nSphere, d->nSquare, d->nCube, d->nTri, d->nVert, s->d_idx, dInfo);
+        plan::counts_kernel<<<grid, 256>>>(s->d_bvh, n, cnt, leafTotal, arrivals);
+        plan::number_kernel<<<grid, 256>>>(s->d_bvh, n, cnt, leafTotal, s->d_ref, pre, dInfo);
+        plan::top_block_kernel<<<1, 1024>>>(s->d_bvh, n, pre, topPos, sortedPre, dInfo);
+        plan::refs_kernel<<<grid, 256>>>(s->d_bvh, n, pre, topPos, sortedPre, s->d_ref, dInfo);
+        g_launches += 5;
+        cudaError_t e = cudaMemcpy(&hostInfo, dInfo, sizeof hostInfo, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "trq_scene_create_device: planning kernels failed: %s", cudaGetErrorString(e)));
+    }
+    if (hostInfo.error)
+        return bail(trq::fail(hostInfo.error == plan::ERR_DEPTH ? TRQ_ERR_DEPTH : TRQ_ERR_LAYOUT, "bvhList: node %u: %s (%u, %u)", hostInfo.errorNode,
+                              plan_error_text(hostInfo.error), hostInfo.errorA, hostInfo.errorB));
+    trq_scene_info_t info{};
+    info.nNode = n; info.nInterior = hostInfo.nInterior; info.nLeaf = hostInfo.nLeaf; info.maxDepth = hostInfo.maxDepth;
+    info.nTri = hostInfo.nTri; info.nSphere = hostInfo.nSphere; info.nSquare = d->nSquare; info.nCube = d->nCube;
+    info.topNodes = hostInfo.nTop;
+    s->maxPIndex = hostInfo.maxPIndex;
+    if ((rc = finish_scene(s, d, info, hostInfo.nSquare, hostInfo.rootRef, hostInfo.rootMin, hostInfo.rootMax)) != TRQ_OK) return bail(rc);
+    *out = s;
+    return TRQ_OK;
+}
+
+// Refit after the vertices moved (animated meshes): same topology, new boxes. The triangle leaves' boxes are recomputed
+// from the new vertices (min / max of the three, AAPLRenderer.mm:575-589), the interior boxes bottom-up as unions of
+// their children (BVH.hh:229-231), and the packed layout is derived again -- all on the device. `triList` holds nVert
+// vertices (device pointer, or host with TRQ_HOST_PTRS). Returns after the scene is ready for the next trq_trace.
+int trq_scene_update_vertices(trq_scene* s, const void* triList, uint32_t nVert, uint32_t flags) {
+    if (!s || !triList) return trq::fail(TRQ_ERR_INVALID, "trq_scene_update_vertices: NULL argument");
+    if (nVert != s->nVert) return trq::fail(TRQ_ERR_INVALID, "trq_scene_update_vertices: %u vertices, the scene has %u", nVert, s->nVert);
+    if (s->nNode < 2 || nVert == 0) return TRQ_OK;
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", s->device);
+    TRQ_CUDA(cudaDeviceSynchronize());                           // traces in flight still read the old boxes
+    TRQ_CUDA(cudaMemcpy(s->d_verts, triList, (size_t)nVert * sizeof(RefVertex), (flags & TRQ_HOST_PTRS) ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice));
+    const uint32_t n = s->nNode;
+    {
+        trq::PoolScratch mem(s->device, nullptr);
+        uint32_t* arrivals;
+        if (!mem.alloc(&arrivals, n)) return trq::fail(TRQ_ERR_NOMEM, "trq_scene_update_vertices: out of device memory");
+        TRQ_CUDA(cudaMemsetAsync(arrivals, 0, (size_t)n * 4));
+        const unsigned grid = (n + 255) / 256;
+        plan::refit_leaves_kernel<<<grid, 256>>>(s->d_bvh, n, s->d_verts, s->d_idx);
+        plan::refit_interior_kernel<<<grid, 256>>>(s->d_bvh, n, arrivals);
+        pack_scene_kernel<<<grid, 256>>>(s->d_bvh, s->d_ref, n, s->d_verts, s->d_idx, s->d_spheres, s->d_squares,
+                                         s->d_nodes, s->d_tris, s->d_sph, s->d_sq, s->d_triN, s->d_topSoA, s->topStride);
+        g_launches += 3;
+        RefAABB root;
+        TRQ_CUDA(cudaMemcpy(&root, &s->d_bvh[0].bBOX, sizeof root, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = root.mini[k]; s->dev.rootMax[k] = root.maxi[k]; }
+    }
+    TRQ_CUDA(cudaGetLastError());
     return TRQ_OK;
 }
 

@@ -60,6 +60,44 @@ class Primitive:
         return sum(a.nbytes for a in (self.sphereList, self.squareList, self.cubeList, self.triList, self.idxList, self.bvhList))
 
 
+class DevicePrimitive:
+    """`struct Primitive` whose six arrays already live on a GPU: torch uint8 CUDA tensors (or None) holding the reference
+    byte layouts. Scene(DevicePrimitive) goes through trq_scene_create_device: nothing crosses PCIe."""
+
+    _sizes = (("sphereList", L.sphere_dtype.itemsize), ("squareList", L.square_dtype.itemsize), ("cubeList", L.cube_dtype.itemsize),
+              ("triList", L.vertex_dtype.itemsize), ("idxList", 12), ("bvhList", L.bvh_dtype.itemsize))
+
+    def __init__(self, sphereList=None, squareList=None, cubeList=None, triList=None, idxList=None, bvhList=None):
+        self.arrays = dict(sphereList=sphereList, squareList=squareList, cubeList=cubeList, triList=triList, idxList=idxList, bvhList=bvhList)
+        for k, item in self._sizes:
+            t = self.arrays[k]
+            if t is not None and (not t.is_cuda or not t.is_contiguous() or t.numel() * t.element_size() % item):
+                raise TypeError(f"{k}: expected a contiguous CUDA tensor holding whole {item}-byte records")
+
+    @classmethod
+    def from_host(cls, prim, device):
+        """Uploads a host Primitive (for tests / for callers that build on the host but create on the device)."""
+        import torch
+        def up(a):
+            return None if a.size == 0 else torch.from_numpy(a.view(np.uint8).reshape(-1).copy()).to(device)
+        return cls(up(prim.sphereList), up(prim.squareList), up(prim.cubeList), up(prim.triList), up(prim.idxList), up(prim.bvhList))
+
+    def count(self, k):
+        t = self.arrays[k]
+        return 0 if t is None else t.numel() * t.element_size() // dict(self._sizes)[k]
+
+    def desc(self):
+        d = SceneDesc()
+        ptr = lambda k: None if self.arrays[k] is None else self.arrays[k].data_ptr()
+        d.sphereList, d.nSphere = ptr("sphereList"), self.count("sphereList")
+        d.squareList, d.nSquare = ptr("squareList"), self.count("squareList")
+        d.cubeList, d.nCube = ptr("cubeList"), self.count("cubeList")
+        d.triList, d.nVert = ptr("triList"), self.count("triList")
+        d.idxList, d.nTri = ptr("idxList"), self.count("idxList")
+        d.bvhList, d.nNode = ptr("bvhList"), self.count("bvhList")
+        return d
+
+
 class BVHBuilder:
     """BVH::buildNode / BVH::buildTree (BVH.hh:246-314): leaves are appended, then the tree is built."""
 
@@ -103,6 +141,21 @@ class BVHBuilder:
         self.maxDepth = depth.value
         return nodes[: nNode.value]
 
+    def buildTreeDevice(self, device=0):
+        """BVH::buildTree with the node array left ON the GPU (trq_bvh_build_tree_device): returns a torch uint8 CUDA
+        tensor holding the 2n-1 64-byte nodes, ready for DevicePrimitive(bvhList=...)."""
+        import torch
+        leaves = np.concatenate(self._chunks) if self._chunks else np.zeros(0, dtype=L.bvh_dtype)
+        n = leaves.size
+        if n == 0:
+            raise ValueError("buildTree: no leaves")
+        d = torch.zeros((2 * n - 1) * L.bvh_dtype.itemsize, dtype=torch.uint8, device=f"cuda:{device}")
+        d[: n * L.bvh_dtype.itemsize] = torch.from_numpy(leaves.view(np.uint8).reshape(-1)).to(d.device)
+        nNode, depth = C.c_uint32(0), C.c_uint32(0)
+        check(lib.trq_bvh_build_tree_device(d.data_ptr(), n, int(device), C.byref(nNode), C.byref(depth)), "trq_bvh_build_tree_device")
+        self.maxDepth = depth.value
+        return d
+
 
 class Scene:
     """`Scene { primitives }` (Render.hh:132-134), resident on one GPU."""
@@ -111,7 +164,10 @@ class Scene:
         self.primitives = primitives
         self._h = C.c_void_p(None)
         d = primitives.desc()
-        check(lib.trq_scene_create(C.byref(d), int(device), C.byref(self._h)), "trq_scene_create")
+        if isinstance(primitives, DevicePrimitive):
+            check(lib.trq_scene_create_device(C.byref(d), int(device), C.byref(self._h)), "trq_scene_create_device")
+        else:
+            check(lib.trq_scene_create(C.byref(d), int(device), C.byref(self._h)), "trq_scene_create")
         self.device = int(device)
         info = SceneInfo()
         check(lib.trq_scene_info(self._h, C.byref(info)), "trq_scene_info")
@@ -148,6 +204,15 @@ class Scene:
         st = stream if stream is not None else torch.cuda.current_stream(rays.device).cuda_stream
         check(lib.trq_trace(self._h, rays.data_ptr(), n, flags, hits.data_ptr(), C.c_void_p(st)), "trq_trace")
         return hits
+
+    def update_vertices(self, triList):
+        """Refit after the vertices moved (same topology): numpy `vertex_dtype` array or a torch uint8 CUDA tensor."""
+        if isinstance(triList, np.ndarray):
+            a = np.ascontiguousarray(triList)
+            check(lib.trq_scene_update_vertices(self._h, a.ctypes.data, a.size, L.HOST_PTRS), "trq_scene_update_vertices")
+        else:
+            n = triList.numel() * triList.element_size() // L.vertex_dtype.itemsize
+            check(lib.trq_scene_update_vertices(self._h, triList.data_ptr(), n, 0), "trq_scene_update_vertices")
 
     @staticmethod
     def kernel_configs():
