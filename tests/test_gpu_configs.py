@@ -80,9 +80,9 @@ def test_hit16_is_the_packed_form_of_trq_hit(built, port):
         scene.close()
 
 
-def test_host_path_tapered_chunks(built):
-    """TRQ_HOST_PTRS cuts a large batch into chunks that ramp up and down (1/8, 1/4, 1/2, 1 ... 1, 1/2, 1/4, 1/8);
-    every ray must land at its own index for sizes around the chunk boundaries."""
+def test_host_path_chunk_boundaries(built):
+    """TRQ_HOST_PTRS cuts a large batch into chunks that cycle through four staging buffers; every ray must land at its own
+    index for sizes around the chunk boundaries, for both record formats."""
     import os
     torch = _torch()
     from tracer_b200 import Scene, harness as H, rays_to_torch

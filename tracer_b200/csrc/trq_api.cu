@@ -127,10 +127,7 @@ struct trq_scene {
     uint64_t stageCap = 0;
     trq_ray* d_stageRays[kStageBufs] = {};
     trq_hit* d_stageHits[kStageBufs] = {};
-    cudaStream_t stageStream[kStageBufs] = {};   // one compute stream per staging buffer (the tails of consecutive chunk kernels overlap)
-    cudaStream_t stageIn = nullptr, stageOut = nullptr;   // ALL H2D copies on one stream, all D2H copies on another: each copy
-                                                          // engine runs its copies back to back at full link rate
-    cudaEvent_t evIn[kStageBufs] = {}, evTraced[kStageBufs] = {}, evOut[kStageBufs] = {};
+    cudaStream_t stageStream[kStageBufs] = {};   // one stream per staging buffer: copy in, trace, copy out in stream order
     bool stageReady = false;
     uint64_t stageSeq = 0;        // chunks ever staged (ring position)
     // optional per-kernel timing (trq_profile_enable): events around the trace and resolve kernels
@@ -152,12 +149,7 @@ void free_scene(trq_scene* s) {
     for (int b = 0; b < kStageBufs; ++b) {
         cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
         if (s->stageStream[b]) cudaStreamDestroy(s->stageStream[b]);
-        if (s->evIn[b]) cudaEventDestroy(s->evIn[b]);
-        if (s->evTraced[b]) cudaEventDestroy(s->evTraced[b]);
-        if (s->evOut[b]) cudaEventDestroy(s->evOut[b]);
     }
-    if (s->stageIn) cudaStreamDestroy(s->stageIn);
-    if (s->stageOut) cudaStreamDestroy(s->stageOut);
     for (int k = 0; k < kProfRing; ++k)
         for (int j = 0; j < 3; ++j) if (s->evProf[k][j]) cudaEventDestroy(s->evProf[k][j]);
     delete s;
@@ -403,23 +395,14 @@ void timeline_dump() {
 #endif
 
 int sync_staging(trq_scene* s) {
-    if (s->stageOut) TRQ_CUDA(cudaStreamSynchronize(s->stageOut));   // the last D2H of every chunk: everything before it is done
     for (int b = 0; b < kStageBufs; ++b)
         if (s->stageStream[b]) TRQ_CUDA(cudaStreamSynchronize(s->stageStream[b]));
-    if (s->stageIn) TRQ_CUDA(cudaStreamSynchronize(s->stageIn));
     return TRQ_OK;
 }
 
 int ensure_staging(trq_scene* s, uint64_t chunk) {
     if (!s->stageReady) {
-        TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageIn, cudaStreamNonBlocking));
-        TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageOut, cudaStreamNonBlocking));
-        for (int b = 0; b < kStageBufs; ++b) {
-            TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageStream[b], cudaStreamNonBlocking));
-            TRQ_CUDA(cudaEventCreateWithFlags(&s->evIn[b], cudaEventDisableTiming));
-            TRQ_CUDA(cudaEventCreateWithFlags(&s->evTraced[b], cudaEventDisableTiming));
-            TRQ_CUDA(cudaEventCreateWithFlags(&s->evOut[b], cudaEventDisableTiming));
-        }
+        for (int b = 0; b < kStageBufs; ++b) TRQ_CUDA(cudaStreamCreateWithFlags(&s->stageStream[b], cudaStreamNonBlocking));
         s->stageReady = true;
     }
     if (chunk > s->stageCap) {
@@ -439,23 +422,18 @@ int ensure_staging(trq_scene* s, uint64_t chunk) {
     return TRQ_OK;
 }
 
-// Host-pointer path: the batch is cut into chunks; chunk k uses staging buffer b = k % kStageBufs. Three stages,
-// chained by events per buffer:
-//   copy-in stream   H2D of the rays (after the kernel that last read this buffer)            -> evIn[b]
-//   stream of b      the trace (after evIn[b] and after the D2H that last read this buffer)   -> evTraced[b]
-//   copy-out stream  D2H of the records (after evTraced[b])                                   -> evOut[b]
-// Every H2D copy is on ONE stream and every D2H copy on another, so each copy engine runs its copies back to back at the
-// full link rate (with one stream per chunk, the H2D copies of 2-3 chunks shared the link and finished late: 41 GB/s
-// instead of 48.5 GB/s, profiles/r02_e2e_timeline_before.txt); kernels of consecutive chunks overlap their tails.
-// A synchronous call pays one chunk of H2D before anything overlaps and one chunk of trace + D2H after the last copy
-// in; the chunk sizes therefore ramp up at the front and down at the back (1/8, 1/4, 1/2, 1, ..., 1, 1/2, 1/4, 1/8).
+// Host-pointer path: the batch is cut into chunks; chunk k goes through staging buffer k % kStageBufs on that
+// buffer's own stream (copy in, trace, copy out, in stream order). Different chunks overlap on the two copy engines
+// and the SMs, buffer reuse is ordered by the stream itself, and a chunk costs four driver calls.
+// Measured alternatives that did not beat it on B200 (profiles/r02_e2e_staging_experiment.txt): all H2D copies on one
+// dedicated stream and all D2H copies on another, chained to the kernels by events (-4 %); chunk sizes ramping up at the
+// front and down at the back of a synchronous call (no change). With a 16-byte record (TRQ_HIT16) the D2H side halves.
 int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, void* hits) {
     const uint64_t chunkRays = [] {                           // read per call so that one process can sweep it
         const char* e = getenv("TRQ_CHUNK_RAYS");
         long long v = e ? atoll(e) : (TRQ_DEFAULT_CHUNK_RAYS)  /* B200 sweep: profiles/r01_e2e_chunk_sweep.txt */;
         return (uint64_t)(v < 1024 ? 1024 : v);
     }();
-    static const int taperEnv = [] { const char* e = getenv("TRQ_CHUNK_TAPER"); return e ? atoi(e) : 1; }();
     const size_t recBytes = (flags & TRQ_HIT16) ? sizeof(trq_hit16) : sizeof(trq_hit);
     std::lock_guard<std::mutex> lock(s->stageMutex);
     // a sorted chunk is only as coherent as it is large: C5 e2e 461 / 605 / 599 / 504 Mrays/s at 512K / 1M / 2M / 4M rays
@@ -463,43 +441,26 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, vo
     const uint64_t chunk = n < want ? n : want;
     int rc = ensure_staging(s, chunk);
     if (rc != TRQ_OK) return rc;
-    const bool taper = taperEnv && !(flags & (TRQ_SORT_RAYS | TRQ_HOST_ASYNC)) && n >= 6 * chunk && chunk >= 8192;
-    std::vector<uint64_t> sizes;
-    if (taper) {
-        const uint64_t ramp[3] = {chunk / 8, chunk / 4, chunk / 2};
-        uint64_t mid = n - 2 * (ramp[0] + ramp[1] + ramp[2]);
-        sizes.assign(ramp, ramp + 3);
-        while (mid) { const uint64_t m = mid < chunk ? mid : chunk; sizes.push_back(m); mid -= m; }
-        for (int r = 2; r >= 0; --r) sizes.push_back(ramp[r]);
-    } else {
-        for (uint64_t left = n; left; ) { const uint64_t m = left < chunk ? left : chunk; sizes.push_back(m); left -= m; }
-    }
     uint64_t done = 0;
-    for (const uint64_t m : sizes) {
+    while (done < n) {
+        const uint64_t m = (n - done) < chunk ? (n - done) : chunk;
         const int b = (int)(s->stageSeq++ % kStageBufs);       // runs across calls: TRQ_HOST_ASYNC calls share the ring
         cudaStream_t st = s->stageStream[b];
 #ifdef TRQ_STAGE_TIMELINE
-        cudaEvent_t* tl = timeline_events(4); cudaEventRecord(tl[0], s->stageIn);
+        cudaEvent_t* tl = timeline_events(4); cudaEventRecord(tl[0], st);
 #endif
-        TRQ_CUDA(cudaStreamWaitEvent(s->stageIn, s->evTraced[b], 0));          // the kernel that last read these staged rays
-        TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, s->stageIn));
-        TRQ_CUDA(cudaEventRecord(s->evIn[b], s->stageIn));
+        TRQ_CUDA(cudaMemcpyAsync(s->d_stageRays[b], rays + done, m * sizeof(trq_ray), cudaMemcpyHostToDevice, st));
 #ifdef TRQ_STAGE_TIMELINE
-        cudaEventRecord(tl[1], s->stageIn);
+        cudaEventRecord(tl[1], st);
 #endif
-        TRQ_CUDA(cudaStreamWaitEvent(st, s->evIn[b], 0));
-        TRQ_CUDA(cudaStreamWaitEvent(st, s->evOut[b], 0));                     // the D2H that last read these staged records
         rc = launch_trace(s, s->d_stageRays[b], m, flags, s->d_stageHits[b], st);
         if (rc != TRQ_OK) return rc;
-        TRQ_CUDA(cudaEventRecord(s->evTraced[b], st));
 #ifdef TRQ_STAGE_TIMELINE
         cudaEventRecord(tl[2], st);
 #endif
-        TRQ_CUDA(cudaStreamWaitEvent(s->stageOut, s->evTraced[b], 0));
-        TRQ_CUDA(cudaMemcpyAsync((uint8_t*)hits + done * recBytes, s->d_stageHits[b], m * recBytes, cudaMemcpyDeviceToHost, s->stageOut));
-        TRQ_CUDA(cudaEventRecord(s->evOut[b], s->stageOut));
+        TRQ_CUDA(cudaMemcpyAsync((uint8_t*)hits + done * recBytes, s->d_stageHits[b], m * recBytes, cudaMemcpyDeviceToHost, st));
 #ifdef TRQ_STAGE_TIMELINE
-        cudaEventRecord(tl[3], s->stageOut);
+        cudaEventRecord(tl[3], st);
 #endif
         done += m;
     }
