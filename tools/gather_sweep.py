@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Developer tool (torchrun, one rank per GPU): C3 step with every rank's hits gathered on every rank, through
-trq_trace_gather (peer stores from the resolve kernel) and through NCCL (dist.trace_and_gather)."""
+trq_trace_gather (peer stores issued by the traversal kernel as each ray retires; 32-byte and 16-byte records) and
+through NCCL (dist.trace_and_gather)."""
 import os
 import sys
 
@@ -39,10 +40,13 @@ ms = timed(lambda: scene.hit(rays, out=out))
 if rank == 0:
     print(f"world {world}  n/rank {n}  no gather: {ms:.3f} ms  {n * world / ms / 1e3:.0f} Mrays/s", flush=True)
 hg = D.HitGather(scene, n)
-ms = timed(lambda: (hg.trace(rays), hg.wait()))
-hg.status()
-if rank == 0:
-    print(f"trq_trace_gather: {ms:.3f} ms  {n * world / ms / 1e3:.0f} Mrays/s", flush=True)
+for h16 in (False, True):
+    ms = timed(lambda: (hg.trace(rays, hit16=h16), hg.wait()))
+    hg.status()
+    if rank == 0:
+        rec = 16 if h16 else 32
+        print(f"trq_trace_gather, {rec}-byte records: {ms:.3f} ms  {n * world / ms / 1e3:.0f} Mrays/s  "
+              f"(NVLink egress per GPU {n * (world - 1) * rec / ms / 1e6:.0f} GB/s)", flush=True)
 hg.close()
 g_all = torch.empty((world, n, 8), dtype=torch.float32, device=dev)
 ms = timed(lambda: D.trace_and_gather(scene, rays, out, g_all))

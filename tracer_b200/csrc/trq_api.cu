@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -43,6 +44,23 @@ namespace {
         if (e_ != cudaSuccess)                                                                  \
             return trq::fail(TRQ_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
+
+// developer instrumentation (tools/build_variant.sh timing -DTRQ_CREATE_TIMING): wall time of the stages of scene creation
+#ifdef TRQ_CREATE_TIMING
+struct StageTimer {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  [create] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+#define TRQ_LAP(timer, what) (timer).lap(what)
+#else
+struct StageTimer {};
+#define TRQ_LAP(timer, what) ((void)(timer))
+#endif
 
 struct DeviceGuard {
     int prev = -1;
@@ -523,6 +541,7 @@ int check_desc(const trq_scene_desc* d, trq_scene** out, const char* who) {
 int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, uint32_t nSqLeaf, uint32_t rootRef,
                  const float rootMin[3], const float rootMax[3]) {
     const int device = s->device;
+    StageTimer tm;
     const size_t nodeBytes = (size_t)info.nInterior * 64, triBytes = (size_t)info.nTri * 16 * TRQ_TRI_STRIDE, sphBytes = (size_t)info.nSphere * 32;
     const size_t sqBytes = (size_t)nSqLeaf * 16 * TRQ_SQ_STRIDE;
     if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes);
@@ -536,6 +555,7 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
     if (cudaMemset(s->d_queues, 0, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMemset(queue heads) failed");
 
     s->nNode = d->nNode; s->nVert = d->nVert; s->topStride = info.topNodes;
+    TRQ_LAP(tm, "allocate packed arrays");
     {
         const unsigned block = 256, grid = (d->nNode + block - 1) / block;
         pack_scene_kernel<<<grid, block>>>(s->d_bvh, s->d_ref, d->nNode, s->d_verts, s->d_idx, s->d_spheres, s->d_squares,
@@ -545,6 +565,7 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
         if (e != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "pack_scene_kernel failed: %s", cudaGetErrorString(e));
     }
 
+    TRQ_LAP(tm, "pack_scene_kernel");
     s->dev.spheres = s->d_spheres; s->dev.squares = s->d_squares; s->dev.cubes = s->d_cubes;
     s->dev.verts = s->d_verts; s->dev.idx = s->d_idx; s->dev.bvh = s->d_bvh;
     s->dev.topSoA = s->d_topSoA; s->dev.topStride = info.topNodes;
@@ -564,6 +585,7 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
         if (e == cudaSuccess) e = cudaMemPoolSetAttribute(s->scratchPool, cudaMemPoolAttrReleaseThreshold, &keep);
         if (e != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(e));
     }
+    TRQ_LAP(tm, "scratch pool");
     // launch configurations: per-CTA shared memory = staged top-of-tree nodes + far-child stack + cold per-ray words
     for (int c = 0; c < kNumCfgs; ++c) {
         const KernelCfg& K = kCfgs[c];
@@ -596,6 +618,7 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
         }
     }
     if (!s->cfg[0].usable) return trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->cfg[0].smem);
+    TRQ_LAP(tm, "kernel configurations");
     // Staging the top of the tree pays when the staged block is a large share of the tree (C1 +15 %, C2 +2-3 %) and loses on
     // 1 M+ triangle scenes (profiles/r02_top_of_tree_experiment.txt): chosen for small trees only.
     s->autoCfg = 0;
@@ -688,6 +711,8 @@ int trq_scene_create_device(const trq_scene_desc* d, int device, trq_scene** out
     DeviceGuard guard(device);
     auto bail = [&](int code) { free_scene(s); return code; };
     if (!guard.ok) return bail(trq::fail(TRQ_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+    StageTimer tm;
+    TRQ_LAP(tm, "open scene");
     const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
     if ((rc = upload_from(&s->d_spheres, d->sphereList, d->nSphere, k)) != TRQ_OK) return bail(rc);
     if ((rc = upload_from(&s->d_squares, d->squareList, d->nSquare, k)) != TRQ_OK) return bail(rc);
@@ -697,6 +722,7 @@ int trq_scene_create_device(const trq_scene_desc* d, int device, trq_scene** out
     if ((rc = upload_from(&s->d_bvh, d->bvhList, d->nNode, k)) != TRQ_OK) return bail(rc);
     const uint32_t n = d->nNode;
     if (cudaMalloc((void**)&s->d_ref, (size_t)n * sizeof(uint32_t)) != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(refs) failed"));
+    TRQ_LAP(tm, "copy six arrays D2D");
 
     plan::PlanInfo hostInfo;
     {
@@ -718,6 +744,7 @@ int trq_scene_create_device(const trq_scene_desc* d, int device, trq_scene** out
         cudaError_t e = cudaMemcpy(&hostInfo, dInfo, sizeof hostInfo, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "trq_scene_create_device: planning kernels failed: %s", cudaGetErrorString(e)));
     }
+    TRQ_LAP(tm, "plan kernels");
     if (hostInfo.error)
         return bail(trq::fail(hostInfo.error == plan::ERR_DEPTH ? TRQ_ERR_DEPTH : TRQ_ERR_LAYOUT, "bvhList: node %u: %s (%u, %u)", hostInfo.errorNode,
                               plan_error_text(hostInfo.error), hostInfo.errorA, hostInfo.errorB));
