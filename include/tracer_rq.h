@@ -165,6 +165,11 @@ int  trq_scene_create_device(const trq_scene_desc* desc, int device, trq_scene**
 int  trq_scene_update_vertices(trq_scene* scene, const void* triList, uint32_t nVert, uint32_t flags);
 
 int  trq_scene_destroy(trq_scene* scene);
+
+/* Scene arrays and builder scratch come from a per-device memory pool that keeps what it is given back (so that
+ * destroy + create of a similar scene, or a rebuild every frame, costs no cudaMalloc). This returns the cached memory of
+ * `device` to the driver. */
+int  trq_device_trim(int device);
 int  trq_scene_info(const trq_scene* scene, trq_scene_info_t* info);
 
 /* Launch configurations of the traversal kernel (tuning knob; results are identical in all of them). A configuration is

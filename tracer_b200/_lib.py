@@ -49,7 +49,7 @@ class Camera(C.Structure):
 # every symbol include/*.h declares; tests/test_abi.py checks the library exports all of them
 ABI_SYMBOLS = [
     "trq_version", "trq_last_error_string", "trq_device_count",
-    "trq_scene_create", "trq_scene_create_device", "trq_scene_update_vertices", "trq_scene_destroy", "trq_scene_info",
+    "trq_scene_create", "trq_scene_create_device", "trq_scene_update_vertices", "trq_scene_destroy", "trq_device_trim", "trq_scene_info",
     "trq_kernel_config_count", "trq_kernel_config_name", "trq_scene_set_kernel_config",
     "trq_trace", "trq_host_sync", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read", "trq_probe_bandwidth",
     "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree", "trq_bvh_build_tree_gpu", "trq_bvh_build_tree_device",
@@ -73,6 +73,7 @@ lib.trq_scene_create.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(_vp)]
 lib.trq_scene_create_device.argtypes = [C.POINTER(SceneDesc), C.c_int, C.POINTER(_vp)]
 lib.trq_scene_update_vertices.argtypes = [_vp, _vp, _u32, _u32]
 lib.trq_scene_destroy.argtypes = [_vp]
+lib.trq_device_trim.argtypes = [C.c_int]
 lib.trq_scene_info.argtypes = [_vp, C.POINTER(SceneInfo)]
 lib.trq_kernel_config_name.argtypes = [C.c_int]
 lib.trq_kernel_config_name.restype = C.c_char_p

@@ -136,7 +136,7 @@ struct trq_scene {
     int defaultCfg = 0, autoCfg = 0;
     // stream-ordered scratch for TRQ_SORT_RAYS: a private pool that keeps its memory across synchronisations
     // (the device's default pool hands it back at every sync and re-maps 64 MB on the next sorted launch)
-    cudaMemPool_t scratchPool = nullptr;
+    cudaMemPool_t scratchPool = nullptr;     // the per-device pool (not owned)
     // ray-queue heads
     QueueHead* d_queues = nullptr;
     std::atomic<uint32_t> queueNext{0};
@@ -157,13 +157,25 @@ struct trq_scene {
 
 namespace {
 
+// Scene arrays come from the per-device pool that keeps its memory (host/scratch.h): a scene created after another one of
+// similar size was destroyed gets its memory back without a cudaMalloc (about 1 ms each for these sizes: 15 of the 22 ms
+// of a 1 M-triangle trq_scene_create_device before). trq_device_trim() hands cached memory back to the driver.
+cudaError_t pool_malloc(void** p, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = trq::scratch_pool(dev);
+    return pool ? cudaMallocFromPoolAsync(p, bytes, pool, nullptr) : cudaMalloc(p, bytes);
+}
+void pool_free(void* p) { if (p) cudaFreeAsync(p, nullptr); }
+
 void free_scene(trq_scene* s) {
     if (!s) return;
-    cudaFree(s->d_spheres); cudaFree(s->d_squares); cudaFree(s->d_cubes);
-    cudaFree(s->d_verts); cudaFree(s->d_idx); cudaFree(s->d_bvh);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_sph); cudaFree(s->d_sq); cudaFree(s->d_triN); cudaFree(s->d_topSoA); cudaFree(s->d_ref);
-    cudaFree(s->d_queues);
-    if (s->scratchPool) cudaMemPoolDestroy(s->scratchPool);
+    cudaDeviceSynchronize();                                   // launches on any stream may still read the arrays
+    pool_free(s->d_spheres); pool_free(s->d_squares); pool_free(s->d_cubes);
+    pool_free(s->d_verts); pool_free(s->d_idx); pool_free(s->d_bvh);
+    pool_free(s->d_nodes); pool_free(s->d_tris); pool_free(s->d_sph); pool_free(s->d_sq); pool_free(s->d_triN); pool_free(s->d_topSoA); pool_free(s->d_ref);
+    pool_free(s->d_queues);
     for (int b = 0; b < kStageBufs; ++b) {
         cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
         if (s->stageStream[b]) cudaStreamDestroy(s->stageStream[b]);
@@ -177,7 +189,7 @@ template <typename T>
 int upload(T** dst, const void* src, size_t count) {
     *dst = nullptr;
     if (count == 0) return TRQ_OK;
-    TRQ_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
+    TRQ_CUDA(pool_malloc((void**)dst, count * sizeof(T)));
     TRQ_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
     return TRQ_OK;
 }
@@ -520,8 +532,8 @@ template <typename T>
 int upload_from(T** dst, const void* src, size_t count, cudaMemcpyKind kind) {
     *dst = nullptr;
     if (count == 0) return TRQ_OK;
-    TRQ_CUDA(cudaMalloc((void**)dst, count * sizeof(T)));
-    TRQ_CUDA(cudaMemcpy(*dst, src, count * sizeof(T), kind));
+    TRQ_CUDA(pool_malloc((void**)dst, count * sizeof(T)));
+    TRQ_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), kind, nullptr));
     return TRQ_OK;
 }
 
@@ -544,15 +556,15 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
     StageTimer tm;
     const size_t nodeBytes = (size_t)info.nInterior * 64, triBytes = (size_t)info.nTri * 16 * TRQ_TRI_STRIDE, sphBytes = (size_t)info.nSphere * 32;
     const size_t sqBytes = (size_t)nSqLeaf * 16 * TRQ_SQ_STRIDE;
-    if (nodeBytes && cudaMalloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes);
-    if (triBytes && cudaMalloc((void**)&s->d_tris, triBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes);
-    if (sphBytes && cudaMalloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes);
-    if (sqBytes && cudaMalloc((void**)&s->d_sq, sqBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(squares %zu B) failed", sqBytes);
+    if (nodeBytes && pool_malloc((void**)&s->d_nodes, nodeBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(nodes %zu B) failed", nodeBytes);
+    if (triBytes && pool_malloc((void**)&s->d_tris, triBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(tris %zu B) failed", triBytes);
+    if (sphBytes && pool_malloc((void**)&s->d_sph, sphBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(spheres %zu B) failed", sphBytes);
+    if (sqBytes && pool_malloc((void**)&s->d_sq, sqBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(squares %zu B) failed", sqBytes);
     const size_t triNBytes = (size_t)info.nTri * 64;
-    if (triNBytes && cudaMalloc((void**)&s->d_triN, triNBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(triangle normals %zu B) failed", triNBytes);
-    if (info.topNodes && cudaMalloc((void**)&s->d_topSoA, (size_t)info.topNodes * 64) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(top-of-tree block) failed");
-    if (cudaMalloc((void**)&s->d_queues, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(queue heads) failed");
-    if (cudaMemset(s->d_queues, 0, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMemset(queue heads) failed");
+    if (triNBytes && pool_malloc((void**)&s->d_triN, triNBytes) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(triangle normals %zu B) failed", triNBytes);
+    if (info.topNodes && pool_malloc((void**)&s->d_topSoA, (size_t)info.topNodes * 64) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(top-of-tree block) failed");
+    if (pool_malloc((void**)&s->d_queues, kQueueRing * sizeof(QueueHead)) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMalloc(queue heads) failed");
+    if (cudaMemsetAsync(s->d_queues, 0, kQueueRing * sizeof(QueueHead), nullptr) != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMemset(queue heads) failed");
 
     s->nNode = d->nNode; s->nVert = d->nVert; s->topStride = info.topNodes;
     TRQ_LAP(tm, "allocate packed arrays");
@@ -574,17 +586,8 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
     for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = rootMin[k]; s->dev.rootMax[k] = rootMax[k]; }
     s->dev.nNode = d->nNode;
     s->stackDepth = info.maxDepth + 1;
-    {
-        cudaMemPoolProps pp = {};
-        pp.allocType = cudaMemAllocationTypePinned;
-        pp.handleTypes = cudaMemHandleTypeNone;
-        pp.location.type = cudaMemLocationTypeDevice;
-        pp.location.id = device;
-        cudaError_t e = cudaMemPoolCreate(&s->scratchPool, &pp);
-        unsigned long long keep = ~0ull;
-        if (e == cudaSuccess) e = cudaMemPoolSetAttribute(s->scratchPool, cudaMemPoolAttrReleaseThreshold, &keep);
-        if (e != cudaSuccess) return trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(e));
-    }
+    s->scratchPool = trq::scratch_pool(device);                // TRQ_SORT_RAYS scratch: stream-ordered, kept between launches
+    if (!s->scratchPool) return trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed");
     TRQ_LAP(tm, "scratch pool");
     // launch configurations: per-CTA shared memory = staged top-of-tree nodes + far-child stack + cold per-ray words
     for (int c = 0; c < kNumCfgs; ++c) {
@@ -642,9 +645,7 @@ int open_scene(int device, trq_scene** sOut, const char* who) {
     trq_scene* s = new (std::nothrow) trq_scene();
     if (!s) return trq::fail(TRQ_ERR_NOMEM, "%s: out of host memory", who);
     s->device = device;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete s; return trq::fail(TRQ_ERR_CUDA, "cudaGetDeviceProperties failed"); }
-    s->numSMs = prop.multiProcessorCount;
+    if (cudaDeviceGetAttribute(&s->numSMs, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) { delete s; return trq::fail(TRQ_ERR_CUDA, "cudaDeviceGetAttribute failed"); }
     *sOut = s;
     return TRQ_OK;
 }
@@ -721,7 +722,7 @@ int trq_scene_create_device(const trq_scene_desc* d, int device, trq_scene** out
     if ((rc = upload_from(&s->d_idx, d->idxList, (size_t)d->nTri * 3, k)) != TRQ_OK) return bail(rc);
     if ((rc = upload_from(&s->d_bvh, d->bvhList, d->nNode, k)) != TRQ_OK) return bail(rc);
     const uint32_t n = d->nNode;
-    if (cudaMalloc((void**)&s->d_ref, (size_t)n * sizeof(uint32_t)) != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(refs) failed"));
+    if (pool_malloc((void**)&s->d_ref, (size_t)n * sizeof(uint32_t)) != cudaSuccess) return bail(trq::fail(TRQ_ERR_CUDA, "cudaMalloc(refs) failed"));
     TRQ_LAP(tm, "copy six arrays D2D");
 
     plan::PlanInfo hostInfo;
@@ -794,6 +795,15 @@ int trq_scene_destroy(trq_scene* s) {
     if (!s) return TRQ_OK;
     DeviceGuard guard(s->device);
     free_scene(s);
+    return TRQ_OK;
+}
+
+int trq_device_trim(int device) {
+    cudaMemPool_t pool = trq::scratch_pool(device);
+    if (!pool) return trq::fail(TRQ_ERR_CUDA, "trq_device_trim: no pool for device %d", device);
+    DeviceGuard guard(device);
+    TRQ_CUDA(cudaDeviceSynchronize());
+    TRQ_CUDA(cudaMemPoolTrimTo(pool, 0));
     return TRQ_OK;
 }
 
