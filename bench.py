@@ -514,8 +514,8 @@ def run_reference_arm(a):
 
 
 def measure_gather(D, work, steps, rank, world):
-    """Every rank's hit records delivered to every rank: trq_trace_gather (the traversal kernel stores each finished
-    record to every peer over NVLink as the ray retires), trq_hit and trq_hit16 records, and NCCL's all-gather beside it.
+    """Every rank's hit records delivered to every rank: trq_trace_gather (tiles of finished records shipped to every peer
+    over NVLink while the traversal runs), trq_hit and trq_hit16 records, and NCCL's all-gather beside it.
     A figure whose records do not check out is nulled."""
     import torch
     n_common = int(-D.max_over_ranks(-float(work.n)))                      # ranks trace slightly different batch sizes
@@ -578,8 +578,8 @@ def measure_gather(D, work, steps, rank, world):
     out["value"] = out["trq_hit"]["value"]
     out["ms_per_step"] = out["trq_hit"]["ms_per_step"]
     out["all_slots_match"] = out["trq_hit"]["all_slots_match"] and out["trq_hit16"]["all_slots_match"]
-    out["how"] = ("trq_trace_gather: compute + all-gather in ONE kernel -- each finished record is stored into every rank's buffer over NVLink "
-                  "peer memory as its ray retires (under the traversal), the last CTA publishes (count, step) with release stores")
+    out["how"] = ("trq_trace_gather: the trace kernel counts finished records per 4096-record tile; a sender kernel sharing the SMs with it ships "
+                  "each complete tile to every rank's buffer over NVLink peer memory (coalesced stores, under the traversal) and publishes (count, step)")
     return out
 
 

@@ -260,10 +260,10 @@ int  trq_mgpu_destroy(trq_mgpu* m);
 
 /* ---- multi-GPU: hit gather through NVLink peer memory (one process per GPU, one node) -----------------------
  * Rays shard across ranks with no collective. A consumer that wants EVERY rank's hits whole
- * (the all-gather of trq_hit[N/R] of section 8e) gets them from the traversal kernel itself: as each ray retires, its
- * finished record is stored into slot [rank] of every rank's buffer over NVLink -- the transfer runs under the
- * traversal -- and the kernel's last CTA publishes (count, step) with system-scope release stores. No NCCL call, no
- * second pass over the records.
+ * (the all-gather of trq_hit[N/R] of section 8e) gets them while the traversal is still running: the trace kernel
+ * counts finished records per 4096-record tile, and a sender kernel that shares the SMs with it ships every complete
+ * tile into slot [rank] of every other rank's buffer over NVLink with coalesced stores -- compute and all-gather
+ * overlap tile by tile -- then publishes (count, step) with system-scope release stores. No NCCL call.
  *   1. every rank: trq_gather_create -> 64-byte handle; exchange the handles (any transport, e.g. MPI /
  *      torch.distributed all_gather) into a world*64-byte array in rank order; trq_gather_connect.
  *   2. per step: trq_trace_gather(rays of this rank) then trq_gather_wait -> hitsAll, counts[r]; rank r's records

@@ -264,16 +264,10 @@ struct TraceParams {
     uint32_t       pad0, pad1;
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
-    // Peer fan-out (trq_trace_gather): every finished record is also stored at the same index of nPeer remote buffers
-    // (NVLink peer memory); the last CTA to leave publishes (count, step) to this rank's and every peer's header.
-    uint32_t            nPeer;
-    uint32_t            pad;
-    unsigned long long  step;
-    unsigned long long* ownFlag;
-    unsigned long long* ownCount;
-    void*               peerHits[TRQ_MAX_PEERS];
-    unsigned long long* peerFlag[TRQ_MAX_PEERS];
-    unsigned long long* peerCount[TRQ_MAX_PEERS];
+    // trq_trace_gather: every finished record also counts towards its tile of TRQ_GATHER_TILE consecutive records
+    // (tileDone[index >> shift], after a fence), so that gather_send_kernel -- running beside this kernel -- can ship each
+    // tile to the peer GPUs the moment it is complete. NULL otherwise.
+    uint32_t*           tileDone;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -297,18 +291,16 @@ __device__ __forceinline__ float4 pack_hit16(const float4& o0, const float4& o1)
     return make_float4(o0.x, __uint_as_float(id), o1.x, o1.y);
 }
 
-// One finished record to this rank's buffer and to the same index of every peer's.
+#define TRQ_GATHER_TILE_SHIFT 12u          // 4096 records per tile: 128 KB of trq_hit, 64 KB of trq_hit16
+
+// One finished record to the output buffer (and, under trq_trace_gather, one more record of its tile complete).
 template <int OUT>
 __device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, const float4& o0, const float4& o1) {
-    if (OUT == OUT_HIT32) {
-        stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
-#pragma unroll 1
-        for (uint32_t p = 0; p < P.nPeer; ++p) stg8(reinterpret_cast<trq_hit*>(P.peerHits[p]) + idx, o0, o1);
-    } else {
-        const float4 c = pack_hit16(o0, o1);
-        stg4(reinterpret_cast<float4*>(P.hits) + idx, c);
-#pragma unroll 1
-        for (uint32_t p = 0; p < P.nPeer; ++p) stg4(reinterpret_cast<float4*>(P.peerHits[p]) + idx, c);
+    if (OUT == OUT_HIT32) stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
+    else                  stg4(reinterpret_cast<float4*>(P.hits) + idx, pack_hit16(o0, o1));
+    if (P.tileDone) {
+        __threadfence();                                       // the record before the count that announces it
+        atomicAdd(P.tileDone + (idx >> TRQ_GATHER_TILE_SHIFT), 1u);
     }
 }
 
@@ -624,25 +616,92 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         } while (__popc(__ballot_sync(0xffffffffu, active)) > keepGoing);
     }
 
-    // ---- epilogue: the last CTA to leave re-arms the queue head for the next launch that draws it and, when a gather
-    // is attached, publishes (count, step) to every rank -- after every thread's peer stores are fenced at system scope
-    if (P.ownFlag) __threadfence_system();
+    // ---- epilogue: the last CTA to leave re-arms the queue head for the next launch that draws it
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
         const unsigned int prev = atomicAdd(&P.queue->done, 1u);
         if (prev == gridDim.x - 1) {
             P.queue->head = 0ull;
             P.queue->done = 0u;
-            if (P.ownFlag) {
-                __threadfence_system();
-                *P.ownCount = N;
-                st_release_sys(P.ownFlag, P.step);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// trq_trace_gather, the collective half. Runs BESIDE trace_packed_kernel on a second stream (one 128-thread, 32-register
+// CTA per SM fits next to the five resident trace CTAs) and ships this rank's records to every peer GPU tile by tile, as
+// soon as the trace has finished a tile: coalesced 16-byte loads from the local buffer (L2), coalesced 16-byte stores into
+// the same place of every peer's buffer over NVLink. The all-gather therefore runs under the traversal instead of after it,
+// and with full-line stores instead of one 32-byte store per ray (per-ray peer stores from the trace kernel itself reached
+// 371 GB/s of NVLink egress at 8 GPUs; coalesced tiles reach the 650-700 GB/s the resolve-pass gather of round 1 did).
+// The last CTA to finish publishes (count, step) to every rank with system-scope release stores.
+struct SendParams {
+    const uint4*        src;                               // this rank's slot of its own buffer (records as 16-byte units)
+    uint4*              peer[TRQ_MAX_PEERS];               // the same slot in every other rank's buffer
+    unsigned long long* peerFlag[TRQ_MAX_PEERS];           // flags[rank] on every other rank: last completed step
+    unsigned long long* peerCount[TRQ_MAX_PEERS];          // counts[phase][rank] on every other rank
+    unsigned long long* ownFlag;
+    unsigned long long* ownCount;
+    const uint32_t*     tileDone;                          // records finished per tile (written by the trace kernel)
+    unsigned int*       blocksDone;
+    unsigned int*       status;                            // raised (mapped host memory) if the trace never delivers a tile
+    unsigned long long  n, step, timeoutNs;
+    uint32_t            nPeer, unitsPerRecord;             // 2 for trq_hit, 1 for trq_hit16
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(128, 16)
+gather_send_kernel(const SendParams G) {
+    __shared__ int giveUp;
+    const uint64_t tileRecords = 1ull << TRQ_GATHER_TILE_SHIFT;
+    const uint64_t nTiles = (G.n + tileRecords - 1) >> TRQ_GATHER_TILE_SHIFT;
+    if (threadIdx.x == 0) giveUp = 0;
+    __syncthreads();
+    for (uint64_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const uint64_t first = tile << TRQ_GATHER_TILE_SHIFT;
+        const uint32_t count = (uint32_t)((G.n - first) < tileRecords ? (G.n - first) : tileRecords);
+        if (threadIdx.x == 0) {                              // wait until the trace has finished every record of this tile
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire_gpu_u32(G.tileDone + tile) < count) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > G.timeoutNs) { *G.status = 0x80000000u; giveUp = 1; break; }
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        if (giveUp) break;
+        const uint64_t base = first * G.unitsPerRecord, total = (uint64_t)count * G.unitsPerRecord;
+        for (uint64_t i = threadIdx.x; i < total; i += 256) {     // two 16-byte units in flight per thread
+            const uint4 a = __ldcg(G.src + base + i);
+            const bool two = i + 128 < total;
+            const uint4 b = two ? __ldcg(G.src + base + i + 128) : a;
 #pragma unroll 1
-                for (uint32_t p = 0; p < P.nPeer; ++p) {
-                    *P.peerCount[p] = N;
-                    st_release_sys(P.peerFlag[p], P.step);
-                }
+            for (uint32_t p = 0; p < G.nPeer; ++p) {
+                G.peer[p][base + i] = a;
+                if (two) G.peer[p][base + i + 128] = b;
+            }
+        }
+    }
+    __threadfence_system();                                   // this thread's peer stores before the CTA's arrival
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(G.blocksDone, 1u);
+        if (prev == gridDim.x - 1) {                          // last CTA: every record of this rank is on its way
+            *G.blocksDone = 0u;
+            __threadfence_system();
+            *G.ownCount = G.n;
+            st_release_sys(G.ownFlag, G.step);
+#pragma unroll 1
+            for (uint32_t p = 0; p < G.nPeer; ++p) {
+                *G.peerCount[p] = G.n;
+                st_release_sys(G.peerFlag[p], G.step);
             }
         }
     }

@@ -295,24 +295,14 @@ int pick_cfg(const trq_scene* s) {
     return c;
 }
 
-// Peer fan-out of one trq_trace_gather step (see struct trq_gather below).
-struct GatherLaunch {
-    uint32_t nPeer = 0;
-    unsigned long long step = 0;
-    unsigned long long* ownFlag = nullptr; unsigned long long* ownCount = nullptr;
-    void* peerHits[TRQ_MAX_PEERS] = {};
-    unsigned long long* peerFlag[TRQ_MAX_PEERS] = {};
-    unsigned long long* peerCount[TRQ_MAX_PEERS] = {};
-};
-
 int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, void* d_hits, cudaStream_t st,
-                 const unsigned long long* nPtr = nullptr, const GatherLaunch* gather = nullptr) {
-    if (n == 0 && !gather) return TRQ_OK;
+                 const unsigned long long* nPtr = nullptr, uint32_t* tileDone = nullptr) {
+    if (n == 0) return TRQ_OK;
     const bool hit16 = (flags & TRQ_HIT16) != 0;
     const size_t recBytes = hit16 ? sizeof(trq_hit16) : sizeof(trq_hit);
     constexpr uint64_t kMaxPerLaunch = 1ull << 31;             // the kernels keep a 32-bit ray index per lane
     if (n > kMaxPerLaunch) {
-        if (nPtr || gather) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect / trq_trace_gather: more than 2^31 rays");
+        if (nPtr || tileDone) return trq::fail(TRQ_ERR_INVALID, "trq_trace_indirect / trq_trace_gather: more than 2^31 rays");
         for (uint64_t off = 0; off < n; off += kMaxPerLaunch) {
             const uint64_t m = (n - off) < kMaxPerLaunch ? (n - off) : kMaxPerLaunch;
             const int rc = launch_trace(s, d_rays + off, m, flags, (uint8_t*)d_hits + off * recBytes, st);
@@ -331,7 +321,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     }
     if (prof) TRQ_CUDA(cudaEventRecord(prof[0], st));          // the ordering pass is part of the timed traversal
     if (flags & TRQ_KERNEL_REFLAYOUT) {
-        if (hit16 || gather) return trq::fail(TRQ_ERR_INVALID, "TRQ_KERNEL_REFLAYOUT writes trq_hit records on one device only");
+        if (hit16 || tileDone) return trq::fail(TRQ_ERR_INVALID, "TRQ_KERNEL_REFLAYOUT writes trq_hit records on one device only");
         const unsigned block = 128;
         const uint64_t grid = (n + block - 1) / block;
         if (grid > 0x7fffffffull) return trq::fail(TRQ_ERR_INVALID, "trq_trace: batch too large");
@@ -352,13 +342,15 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
         static const int blocksPerSMOverride =[] { const char* e = getenv("TRQ_BLOCKS_PER_SM"); return e ? atoi(e) : 0; }();
-        const int c = pick_cfg(s);
+        // under trq_trace_gather the sender kernel shares every SM with this one: a one-CTA-per-SM configuration that
+        // takes (nearly) all of an SM's shared memory could be locked out by a resident sender CTA that waits for it
+        const int c = tileDone ? 0 : pick_cfg(s);
         const KernelCfg& K = kCfgs[c];
         const trq_scene::CfgState& cs = s->cfg[c];
         int perSM = cs.blocksPerSM[any ? 1 : 0][hit16 ? 1 : 0];                  // queried once, in trq_scene_create
         if (blocksPerSMOverride > 0 && blocksPerSMOverride < perSM) perSM = blocksPerSMOverride;
         uint64_t grid = (uint64_t)perSM * (uint64_t)s->numSMs;             // persistent: a multiple of the SM count
-        const uint64_t need = n ? (n + K.block - 1) / K.block : 1;          // an empty gather step still publishes
+        const uint64_t need = (n + K.block - 1) / K.block;
         if (grid > need) grid = need;
         TraceParams P{};
         P.rays = d_rays; P.hits = d_hits; P.n = n;
@@ -367,12 +359,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         P.stackDepth = cs.stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
         P.topCount = K.top ? cs.topCount : 0;
         P.order = nullptr; P.nPtr = nPtr;
-        if (gather) {
-            P.nPeer = gather->nPeer; P.step = gather->step; P.ownFlag = gather->ownFlag; P.ownCount = gather->ownCount;
-            for (uint32_t k = 0; k < gather->nPeer; ++k) {
-                P.peerHits[k] = gather->peerHits[k]; P.peerFlag[k] = gather->peerFlag[k]; P.peerCount[k] = gather->peerCount[k];
-            }
-        }
+        P.tileDone = tileDone;
         // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
         // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
         // that does not fit L2); TRQ_SORT_RAYS=0/1 in the environment overrides for experiments.
@@ -1027,9 +1014,10 @@ int trq_spawn_shadow_rng(trq_scene* s, const trq_ray* rays, const trq_hit* hits,
 // ---------------------------------------------------------------------------------------------------------
 // Peer-memory hit gather (a consumer that wants every rank's hits whole). One process per GPU;
 // every rank owns a buffer [phase][rank][capacity] of trq_hit plus a small header (flags, counts), exported through
-// CUDA IPC. trq_trace_gather traces this rank's rays and the trace kernel itself stores each finished record into slot
-// [rank] of EVERY rank's buffer over NVLink as the ray retires -- compute and all-gather are one kernel, the transfer
-// runs under the traversal, no NCCL call and no second pass over the data -- then its last CTA publishes (count, step)
+// CUDA IPC. trq_trace_gather traces this rank's rays into slot [rank] of its own buffer and, BESIDE the trace kernel,
+// runs gather_send_kernel on a second stream: the trace counts finished records per 4096-record tile, the sender ships
+// each complete tile into slot [rank] of EVERY other rank's buffer over NVLink with coalesced 16-byte stores. The
+// all-gather runs under the traversal, tile by tile, with no NCCL call; the sender's last CTA publishes (count, step)
 // with system-scope release stores. trq_gather_wait enqueues a small kernel that acquires all ranks' step numbers.
 // Three phases (step mod 3): a peer can start writing phase p again at step k + 3 only after it has seen this rank's
 // flag for step k + 2, so the result of step k stays valid until this rank's trq_trace_gather for step k + 2 executes.
@@ -1050,6 +1038,11 @@ struct trq_gather {
     unsigned long long step = 0;
     uint32_t lastFlags = 0;
     bool connected = false;
+    cudaStream_t sendStream = nullptr;                 // gather_send_kernel runs here, beside the trace on the caller's stream
+    cudaEvent_t evStart = nullptr, evSent = nullptr;
+    uint32_t* d_tileDone = nullptr;                    // finished records per tile of the step being traced
+    unsigned int* d_blocksDone = nullptr;
+    int numSMs = 0;
     size_t slot_offset(unsigned phase, uint32_t r) const {
         return kGatherHeader + ((size_t)phase * world + r) * capacity * sizeof(trq_hit);
     }
@@ -1075,10 +1068,21 @@ int trq_gather_create(trq_scene* s, uint32_t rank, uint32_t world, uint64_t capa
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&g->h_status, sizeof(unsigned int), cudaHostAllocMapped);
     if (e == cudaSuccess) { *g->h_status = 0; e = cudaHostGetDevicePointer((void**)&g->d_status, g->h_status, 0); }
+    const size_t nTiles = (size_t)((capacity + (1ull << TRQ_GATHER_TILE_SHIFT) - 1) >> TRQ_GATHER_TILE_SHIFT);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_tileDone, (nTiles + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(g->d_tileDone, 0, (nTiles + 1) * sizeof(uint32_t));   // last word: blocksDone
+    if (e == cudaSuccess) { g->d_blocksDone = g->d_tileDone + nTiles; e = cudaStreamCreateWithFlags(&g->sendStream, cudaStreamNonBlocking); }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->evStart, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->evSent, cudaEventDisableTiming);
+    g->numSMs = s->numSMs;
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, g->base);
     if (e != cudaSuccess) {
-        cudaFree(g->base); if (g->h_status) cudaFreeHost(g->h_status); delete g;
+        cudaFree(g->base); cudaFree(g->d_tileDone); if (g->h_status) cudaFreeHost(g->h_status);
+        if (g->sendStream) cudaStreamDestroy(g->sendStream);
+        if (g->evStart) cudaEventDestroy(g->evStart);
+        if (g->evSent) cudaEventDestroy(g->evSent);
+        delete g;
         return trq::fail(TRQ_ERR_CUDA, "trq_gather_create (%zu bytes): %s", total, cudaGetErrorString(e));
     }
     memcpy(handle, &h, sizeof h);
@@ -1116,19 +1120,42 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
     const unsigned long long step = ++g->step;
     const unsigned phase = (unsigned)(step % kGatherPhases);
     g->lastFlags = flags;
-    GatherLaunch G;
-    G.step = step;
+    static const unsigned long long timeoutNs = [] {
+        const char* e = getenv("TRQ_GATHER_TIMEOUT_MS");
+        return (unsigned long long)(e ? atoll(e) : 10000) * 1000000ull;
+    }();
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t* own = g->base + g->slot_offset(phase, g->rank);
+    SendParams G{};
+    G.src = (const uint4*)own;
+    G.n = n; G.step = step; G.timeoutNs = timeoutNs;
+    G.unitsPerRecord = (flags & TRQ_HIT16) ? 1u : 2u;
+    G.tileDone = g->d_tileDone; G.blocksDone = g->d_blocksDone; G.status = g->d_status;
     G.ownFlag = (unsigned long long*)g->base + g->rank;
     G.ownCount = (unsigned long long*)(g->base + kGatherCountsAt) + phase * TRQ_GATHER_MAX_RANKS + g->rank;
     for (uint32_t r = 0; r < g->world; ++r) {
         if (r == g->rank) continue;
         const uint32_t k = G.nPeer++;
-        G.peerHits[k] = g->peerBase[r] + g->slot_offset(phase, g->rank);
+        G.peer[k] = (uint4*)(g->peerBase[r] + g->slot_offset(phase, g->rank));
         G.peerFlag[k] = (unsigned long long*)g->peerBase[r] + g->rank;
         G.peerCount[k] = (unsigned long long*)(g->peerBase[r] + kGatherCountsAt) + phase * TRQ_GATHER_MAX_RANKS + g->rank;
     }
-    void* own = g->base + g->slot_offset(phase, g->rank);
-    return launch_trace(s, rays, n, flags, own, (cudaStream_t)stream, nullptr, &G);
+    const uint64_t nTiles = (n + (1ull << TRQ_GATHER_TILE_SHIFT) - 1) >> TRQ_GATHER_TILE_SHIFT;
+    // the sender starts when the caller's stream reaches this point (its counters zeroed), runs beside the trace, and the
+    // caller's stream continues after both
+    if (nTiles) TRQ_CUDA(cudaMemsetAsync(g->d_tileDone, 0, nTiles * sizeof(uint32_t), st));
+    TRQ_CUDA(cudaEventRecord(g->evStart, st));
+    TRQ_CUDA(cudaStreamWaitEvent(g->sendStream, g->evStart, 0));
+    unsigned sendGrid = (unsigned)g->numSMs;
+    if (nTiles < sendGrid) sendGrid = nTiles ? (unsigned)nTiles : 1u;
+    const int rc = launch_trace(s, rays, n, flags, own, st, nullptr, g->d_tileDone);     // first: its CTAs take their places
+    if (rc != TRQ_OK) return rc;
+    gather_send_kernel<<<sendGrid, 128, 0, g->sendStream>>>(G);
+    g_launches++;
+    TRQ_CUDA(cudaGetLastError());
+    TRQ_CUDA(cudaEventRecord(g->evSent, g->sendStream));
+    TRQ_CUDA(cudaStreamWaitEvent(st, g->evSent, 0));
+    return TRQ_OK;
 }
 
 int trq_gather_wait(trq_gather* g, void* stream, const void** hitsAll, const uint64_t** counts) {
@@ -1151,6 +1178,7 @@ int trq_gather_wait(trq_gather* g, void* stream, const void** hitsAll, const uin
 int trq_gather_status(trq_gather* g) {
     if (!g) return trq::fail(TRQ_ERR_INVALID, "trq_gather_status: NULL gather");
     const unsigned int v = *(volatile unsigned int*)g->h_status;
+    if (v & 0x80000000u) return trq::fail(TRQ_ERR_CUDA, "trq_trace_gather: the trace did not finish a tile before the timeout");
     if (v) return trq::fail(TRQ_ERR_CUDA, "trq_gather_wait: rank %u did not publish its hits before the timeout", v - 1);
     return TRQ_OK;
 }
@@ -1160,6 +1188,10 @@ int trq_gather_destroy(trq_gather* g) {
     DeviceGuard guard(g->scene->device);
     cudaDeviceSynchronize();
     for (uint32_t r = 0; r < g->world; ++r) if (g->peerBase[r]) cudaIpcCloseMemHandle(g->peerBase[r]);
+    if (g->sendStream) cudaStreamDestroy(g->sendStream);
+    if (g->evStart) cudaEventDestroy(g->evStart);
+    if (g->evSent) cudaEventDestroy(g->evSent);
+    cudaFree(g->d_tileDone);
     cudaFree(g->base);
     if (g->h_status) cudaFreeHost(g->h_status);
     delete g;

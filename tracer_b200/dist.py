@@ -194,8 +194,8 @@ class _DevArray:
 
 
 class HitGather:
-    """Hit all-gather fused into the traversal kernel (trq_trace_gather): every rank's records land in every rank's
-    (world, capacity, 8) buffer through NVLink peer stores issued as the rays retire. One process per GPU on one node
+    """Hit all-gather overlapped with the traversal (trq_trace_gather): every rank's records land in every rank's
+    (world, capacity, 8) buffer through NVLink peer stores, tile by tile while the trace runs. One process per GPU on one node
     (two ranks may share one device for tests: CUDA IPC works between processes on the same GPU).
 
         g = HitGather(scene, capacity)          # collective: allocates, exchanges CUDA-IPC handles, connects
