@@ -27,6 +27,7 @@
 #include <cmath>
 #include <cstring>
 #include <future>
+#include <exception>
 #include <vector>
 
 namespace {
@@ -244,12 +245,18 @@ int trq_bvh_build_tree(void* bvhList, uint32_t nLeaves, uint32_t* nNodeOut, uint
     RefBVH* nodes = (RefBVH*)bvhList;
     const uint32_t nNode = 2 * nLeaves - 1;
 
+    // no C++ exception may cross the C ABI: std::vector (bad_alloc) and std::async (system_error when no thread can be
+    // started) both throw
+    try {
     std::vector<uint32_t> idx(nLeaves);                                                    // BVH.hh:248-253
     std::vector<V3> cen(nLeaves);
     for (uint32_t i = 0; i < nLeaves; ++i) { idx[i] = i; cen[i] = centroid_of(nodes[i]); }
 
     Builder b{nodes, idx.data(), cen.data(), nLeaves};
     b.make(0, nLeaves, 0, 0);                                                              // :260
+    } catch (const std::exception& e) {
+        return trq::fail(TRQ_ERR_NOMEM, "trq_bvh_build_tree: %s", e.what());
+    }
 
     // :263-268  move the root (last node) to the front; everything else shifts by +1, which the
     // +1s stored in left/right/parent anticipated.
@@ -262,7 +269,7 @@ int trq_bvh_build_tree(void* bvhList, uint32_t nLeaves, uint32_t* nNodeOut, uint
 
     // deepest interior level (root = 0): the reference's trail has 32 bits (Render.hh:140,172)
     uint32_t maxDepth = 0;
-    if (nLeaves > 1) {
+    if (nLeaves > 1) try {
         std::vector<uint32_t> depth(nNode, 0);
         // parents always have a larger pre-shift index than their children, i.e. interior nodes
         // appear after their descendants except the root at 0: walk from the end to the front.
@@ -274,6 +281,8 @@ int trq_bvh_build_tree(void* bvhList, uint32_t nLeaves, uint32_t* nNodeOut, uint
                 maxDepth = std::max(maxDepth, depth[i]);
             }
         }
+    } catch (const std::exception& e) {
+        return trq::fail(TRQ_ERR_NOMEM, "trq_bvh_build_tree: %s", e.what());
     }
     if (nNodeOut) *nNodeOut = nNode;
     if (maxDepthOut) *maxDepthOut = maxDepth;

@@ -299,8 +299,13 @@ __device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, 
     if (OUT == OUT_HIT32) stg8(reinterpret_cast<trq_hit*>(P.hits) + idx, o0, o1);
     else                  stg4(reinterpret_cast<float4*>(P.hits) + idx, pack_hit16(o0, o1));
     if (P.tileDone) {
-        __threadfence();                                       // the record before the count that announces it
-        atomicAdd(P.tileDone + (idx >> TRQ_GATHER_TILE_SHIFT), 1u);
+        // the record before the count that announces it; lanes of this warp whose records fall into the same tile (nearly
+        // always all of them: a warp draws consecutive queue slots) send ONE count between them -- the whole GPU works on a
+        // handful of tiles at any moment, and per-record atomics on those few addresses serialise in L2
+        __threadfence();
+        const uint32_t tile = idx >> TRQ_GATHER_TILE_SHIFT;
+        const unsigned peers = __match_any_sync(__activemask(), tile);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(P.tileDone + tile, (uint32_t)__popc(peers));
     }
 }
 
@@ -657,14 +662,13 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 
 __global__ void __launch_bounds__(128, 16)
 gather_send_kernel(const SendParams G) {
-    __shared__ int giveUp;
+    // (no shared memory: the CTA has to fit into what five resident trace CTAs leave of the SM's carve-out)
     const uint64_t tileRecords = 1ull << TRQ_GATHER_TILE_SHIFT;
     const uint64_t nTiles = (G.n + tileRecords - 1) >> TRQ_GATHER_TILE_SHIFT;
-    if (threadIdx.x == 0) giveUp = 0;
-    __syncthreads();
     for (uint64_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
         const uint64_t first = tile << TRQ_GATHER_TILE_SHIFT;
         const uint32_t count = (uint32_t)((G.n - first) < tileRecords ? (G.n - first) : tileRecords);
+        int giveUp = 0;
         if (threadIdx.x == 0) {                              // wait until the trace has finished every record of this tile
             unsigned long long t0;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -675,8 +679,7 @@ gather_send_kernel(const SendParams G) {
                 __nanosleep(200);
             }
         }
-        __syncthreads();
-        if (giveUp) break;
+        if (__syncthreads_or(giveUp)) break;
         const uint64_t base = first * G.unitsPerRecord, total = (uint64_t)count * G.unitsPerRecord;
         for (uint64_t i = threadIdx.x; i < total; i += 256) {     // two 16-byte units in flight per thread
             const uint4 a = __ldcg(G.src + base + i);

@@ -1148,7 +1148,24 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
     TRQ_CUDA(cudaStreamWaitEvent(g->sendStream, g->evStart, 0));
     unsigned sendGrid = (unsigned)g->numSMs;
     if (nTiles < sendGrid) sendGrid = nTiles ? (unsigned)nTiles : 1u;
+    // The sender CTA (no shared memory of its own, 1 KB of per-CTA reserve) must fit beside the resident trace CTAs. The
+    // driver sizes the SM's shared-memory carve-out to what the trace needs, rounded up to a supported size; when that leaves
+    // less than the reserve (C3's depth: 5 x 39 KB = 195 of 196 KB), ask for the next size for this launch.
+    const bool any = (flags & TRQ_TRACE_ANY) != 0, hit16 = (flags & TRQ_HIT16) != 0;
+    const void* fn = kCfgs[0].fn[any ? 1 : 0][hit16 ? 1 : 0];
+    bool bumped = false;
+    if (n) {
+        static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+        const size_t need = (size_t)s->cfg[0].blocksPerSM[any ? 1 : 0][hit16 ? 1 : 0] * (s->cfg[0].smem + kSmemBlockReserve);
+        size_t chosen = 228 * 1024;
+        for (size_t kb : kCarveKB) if (kb * 1024 >= need) { chosen = kb * 1024; break; }
+        if (chosen - need < kSmemBlockReserve + 512 && chosen < 228 * 1024) {
+            for (size_t kb : kCarveKB) if (kb * 1024 > chosen) { chosen = kb * 1024; break; }
+            bumped = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((chosen * 100 + kSmemPerSM - 1) / kSmemPerSM)) == cudaSuccess;
+        }
+    }
     const int rc = launch_trace(s, rays, n, flags, own, st, nullptr, g->d_tileDone);     // first: its CTAs take their places
+    if (bumped) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
     if (rc != TRQ_OK) return rc;
     gather_send_kernel<<<sendGrid, 128, 0, g->sendStream>>>(G);
     g_launches++;
