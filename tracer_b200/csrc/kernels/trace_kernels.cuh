@@ -268,6 +268,7 @@ struct TraceParams {
     // (tileDone[index >> shift], after a fence), so that gather_send_kernel -- running beside this kernel -- can ship each
     // tile to the peer GPUs the moment it is complete. NULL otherwise.
     uint32_t*           tileDone;
+    uint32_t            tileShift;     // log2(records per tile)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -291,7 +292,7 @@ __device__ __forceinline__ float4 pack_hit16(const float4& o0, const float4& o1)
     return make_float4(o0.x, __uint_as_float(id), o1.x, o1.y);
 }
 
-#define TRQ_GATHER_TILE_SHIFT 12u          // 4096 records per tile: 128 KB of trq_hit, 64 KB of trq_hit16
+#define TRQ_GATHER_TILE_SHIFT_MIN 8u       // tile sizes a gather may use: 2^8 .. 2^16 records (default 2^11, trq_api.cu)
 
 // One finished record to the output buffer (and, under trq_trace_gather, one more record of its tile complete).
 template <int OUT>
@@ -303,7 +304,7 @@ __device__ __forceinline__ void emit_record(const TraceParams& P, uint32_t idx, 
         // always all of them: a warp draws consecutive queue slots) send ONE count between them -- the whole GPU works on a
         // handful of tiles at any moment, and per-record atomics on those few addresses serialise in L2
         __threadfence();
-        const uint32_t tile = idx >> TRQ_GATHER_TILE_SHIFT;
+        const uint32_t tile = idx >> P.tileShift;
         const unsigned peers = __match_any_sync(__activemask(), tile);
         if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(P.tileDone + tile, (uint32_t)__popc(peers));
     }
@@ -652,6 +653,7 @@ struct SendParams {
     unsigned int*       status;                            // raised (mapped host memory) if the trace never delivers a tile
     unsigned long long  n, step, timeoutNs;
     uint32_t            nPeer, unitsPerRecord;             // 2 for trq_hit, 1 for trq_hit16
+    uint32_t            tileShift;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
@@ -663,10 +665,10 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
 __global__ void __launch_bounds__(128, 16)
 gather_send_kernel(const SendParams G) {
     // (no shared memory: the CTA has to fit into what five resident trace CTAs leave of the SM's carve-out)
-    const uint64_t tileRecords = 1ull << TRQ_GATHER_TILE_SHIFT;
-    const uint64_t nTiles = (G.n + tileRecords - 1) >> TRQ_GATHER_TILE_SHIFT;
+    const uint64_t tileRecords = 1ull << G.tileShift;
+    const uint64_t nTiles = (G.n + tileRecords - 1) >> G.tileShift;
     for (uint64_t tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-        const uint64_t first = tile << TRQ_GATHER_TILE_SHIFT;
+        const uint64_t first = tile << G.tileShift;
         const uint32_t count = (uint32_t)((G.n - first) < tileRecords ? (G.n - first) : tileRecords);
         int giveUp = 0;
         if (threadIdx.x == 0) {                              // wait until the trace has finished every record of this tile

@@ -296,7 +296,7 @@ int pick_cfg(const trq_scene* s) {
 }
 
 int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, void* d_hits, cudaStream_t st,
-                 const unsigned long long* nPtr = nullptr, uint32_t* tileDone = nullptr) {
+                 const unsigned long long* nPtr = nullptr, uint32_t* tileDone = nullptr, uint32_t tileShift = 0) {
     if (n == 0) return TRQ_OK;
     const bool hit16 = (flags & TRQ_HIT16) != 0;
     const size_t recBytes = hit16 ? sizeof(trq_hit16) : sizeof(trq_hit);
@@ -359,7 +359,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         P.stackDepth = cs.stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
         P.topCount = K.top ? cs.topCount : 0;
         P.order = nullptr; P.nPtr = nPtr;
-        P.tileDone = tileDone;
+        P.tileDone = tileDone; P.tileShift = tileShift;
         // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
         // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
         // that does not fit L2); TRQ_SORT_RAYS=0/1 in the environment overrides for experiments.
@@ -1068,7 +1068,7 @@ int trq_gather_create(trq_scene* s, uint32_t rank, uint32_t world, uint64_t capa
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&g->h_status, sizeof(unsigned int), cudaHostAllocMapped);
     if (e == cudaSuccess) { *g->h_status = 0; e = cudaHostGetDevicePointer((void**)&g->d_status, g->h_status, 0); }
-    const size_t nTiles = (size_t)((capacity + (1ull << TRQ_GATHER_TILE_SHIFT) - 1) >> TRQ_GATHER_TILE_SHIFT);
+    const size_t nTiles = (size_t)((capacity + (1ull << TRQ_GATHER_TILE_SHIFT_MIN) - 1) >> TRQ_GATHER_TILE_SHIFT_MIN);
     if (e == cudaSuccess) e = cudaMalloc((void**)&g->d_tileDone, (nTiles + 1) * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(g->d_tileDone, 0, (nTiles + 1) * sizeof(uint32_t));   // last word: blocksDone
     if (e == cudaSuccess) { g->d_blocksDone = g->d_tileDone + nTiles; e = cudaStreamCreateWithFlags(&g->sendStream, cudaStreamNonBlocking); }
@@ -1140,7 +1140,14 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
         G.peerFlag[k] = (unsigned long long*)g->peerBase[r] + g->rank;
         G.peerCount[k] = (unsigned long long*)(g->peerBase[r] + kGatherCountsAt) + phase * TRQ_GATHER_MAX_RANKS + g->rank;
     }
-    const uint64_t nTiles = (n + (1ull << TRQ_GATHER_TILE_SHIFT) - 1) >> TRQ_GATHER_TILE_SHIFT;
+    // records per tile: small tiles follow the trace closely (short tail after its last ray), large ones cost fewer polls
+    static const uint32_t tileShift = [] {
+        const char* e = getenv("TRQ_GATHER_TILE_SHIFT");
+        int v = e ? atoi(e) : 11;
+        return (uint32_t)(v < (int)TRQ_GATHER_TILE_SHIFT_MIN ? (int)TRQ_GATHER_TILE_SHIFT_MIN : (v > 16 ? 16 : v));
+    }();
+    G.tileShift = tileShift;
+    const uint64_t nTiles = (n + (1ull << tileShift) - 1) >> tileShift;
     // the sender starts when the caller's stream reaches this point (its counters zeroed), runs beside the trace, and the
     // caller's stream continues after both
     if (nTiles) TRQ_CUDA(cudaMemsetAsync(g->d_tileDone, 0, nTiles * sizeof(uint32_t), st));
@@ -1164,7 +1171,7 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
             bumped = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((chosen * 100 + kSmemPerSM - 1) / kSmemPerSM)) == cudaSuccess;
         }
     }
-    const int rc = launch_trace(s, rays, n, flags, own, st, nullptr, g->d_tileDone);     // first: its CTAs take their places
+    const int rc = launch_trace(s, rays, n, flags, own, st, nullptr, g->d_tileDone, tileShift);     // first: its CTAs take their places
     if (bumped) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
     if (rc != TRQ_OK) return rc;
     gather_send_kernel<<<sendGrid, 128, 0, g->sendStream>>>(G);
