@@ -712,6 +712,80 @@ gather_send_kernel(const SendParams G) {
     }
 }
 
+// The same sender with the copy engine of the SM doing the work: one thread per CTA drives TMA bulk copies
+// (cp.async.bulk): tile chunk -> shared memory (completion on an mbarrier), shared memory -> the slot in every peer's
+// buffer over NVLink (bulk async-groups), two chunks in flight. No registers or LSU slots per byte in flight -- the l1tex
+// pipe the trace kernel is bound by is left alone -- and the NVLink writes are full 128-byte lines issued in long bursts.
+#define TRQ_SEND_TMA_STAGES 2u
+#define TRQ_SEND_TMA_CHUNK 12288u          // bytes per stage (2 x 12 KB + 1 KB reserve fit beside the trace CTAs' carve-out)
+
+__global__ void __launch_bounds__(32)
+gather_send_tma_kernel(const SendParams G) {
+    extern __shared__ __align__(128) unsigned char sendBuf[];           // [TRQ_SEND_TMA_STAGES][TRQ_SEND_TMA_CHUNK]
+    __shared__ __align__(8) unsigned long long loadBar[TRQ_SEND_TMA_STAGES];
+    if (threadIdx.x == 0) {
+        for (uint32_t k = 0; k < TRQ_SEND_TMA_STAGES; ++k)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&loadBar[k])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint64_t tileRecords = 1ull << G.tileShift;
+        const uint64_t nTiles = (G.n + tileRecords - 1) >> G.tileShift;
+        const uint32_t recBytes = G.unitsPerRecord * 16u;
+        uint32_t chunkNo = 0;                                             // chunks issued so far: stage = chunkNo % stages
+        bool giveUp = false;
+        for (uint64_t tile = blockIdx.x; tile < nTiles && !giveUp; tile += gridDim.x) {
+            const uint64_t first = tile << G.tileShift;
+            const uint32_t count = (uint32_t)((G.n - first) < tileRecords ? (G.n - first) : tileRecords);
+            unsigned long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire_gpu_u32(G.tileDone + tile) < count) {      // the trace has finished every record of this tile
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > G.timeoutNs) { *G.status = 0x80000000u; giveUp = true; break; }
+                __nanosleep(200);
+            }
+            if (giveUp) break;
+            // records written by st.global on other SMs, read here by the async proxy: order the two
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            const uint64_t tileBytes = (uint64_t)count * recBytes, base = first * recBytes;
+            for (uint64_t off = 0; off < tileBytes; off += TRQ_SEND_TMA_CHUNK, ++chunkNo) {
+                const uint32_t bytes = (uint32_t)((tileBytes - off) < TRQ_SEND_TMA_CHUNK ? (tileBytes - off) : TRQ_SEND_TMA_CHUNK);
+                const uint32_t stage = chunkNo % TRQ_SEND_TMA_STAGES, phase = (chunkNo / TRQ_SEND_TMA_STAGES) & 1u;
+                const uint32_t sm = (uint32_t)__cvta_generic_to_shared(sendBuf + stage * TRQ_SEND_TMA_CHUNK);
+                const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&loadBar[stage]);
+                // the peer stores that last read this stage must have read it
+                asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(TRQ_SEND_TMA_STAGES - 1) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(sm), "l"(reinterpret_cast<const unsigned char*>(G.src) + base + off), "r"(bytes), "r"(mb) : "memory");
+                uint32_t ready = 0;
+                while (!ready)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ready) : "r"(mb), "r"(phase) : "memory");
+#pragma unroll 1
+                for (uint32_t p = 0; p < G.nPeer; ++p)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(reinterpret_cast<unsigned char*>(G.peer[p]) + base + off), "r"(sm), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");       // every peer store of this CTA has been performed
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence_system();
+        const unsigned int prev = atomicAdd(G.blocksDone, 1u);
+        if (prev == gridDim.x - 1) {                          // last CTA: every record of this rank is on its way
+            *G.blocksDone = 0u;
+            __threadfence_system();
+            *G.ownCount = G.n;
+            st_release_sys(G.ownFlag, G.step);
+#pragma unroll 1
+            for (uint32_t p = 0; p < G.nPeer; ++p) {
+                *G.peerCount[p] = G.n;
+                st_release_sys(G.peerFlag[p], G.step);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // compact -> trq_hit, in place, for the reference-layout kernel (the packed kernel finishes its own records).
 // One thread per ray, fully coalesced.

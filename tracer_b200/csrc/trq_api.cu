@@ -1160,13 +1160,16 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
     // less than the reserve (C3's depth: 5 x 39 KB = 195 of 196 KB), ask for the next size for this launch.
     const bool any = (flags & TRQ_TRACE_ANY) != 0, hit16 = (flags & TRQ_HIT16) != 0;
     const void* fn = kCfgs[0].fn[any ? 1 : 0][hit16 ? 1 : 0];
-    bool bumped = false;
+    bool bumped = false, useTma = false;
     if (n) {
         static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
         const size_t need = (size_t)s->cfg[0].blocksPerSM[any ? 1 : 0][hit16 ? 1 : 0] * (s->cfg[0].smem + kSmemBlockReserve);
         size_t chosen = 228 * 1024;
         for (size_t kb : kCarveKB) if (kb * 1024 >= need) { chosen = kb * 1024; break; }
-        if (chosen - need < kSmemBlockReserve + 512 && chosen < 228 * 1024) {
+        static const int tmaEnv = [] { const char* e = getenv("TRQ_GATHER_TMA"); return e ? atoi(e) : 0; }();
+        useTma = tmaEnv != 0;
+        const size_t senderSmem = useTma ? (size_t)TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK + 256 : 0;
+        if (chosen - need < kSmemBlockReserve + 512 + senderSmem && chosen < 228 * 1024) {
             for (size_t kb : kCarveKB) if (kb * 1024 > chosen) { chosen = kb * 1024; break; }
             bumped = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((chosen * 100 + kSmemPerSM - 1) / kSmemPerSM)) == cudaSuccess;
         }
@@ -1174,7 +1177,8 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
     const int rc = launch_trace(s, rays, n, flags, own, st, nullptr, g->d_tileDone, tileShift);     // first: its CTAs take their places
     if (bumped) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
     if (rc != TRQ_OK) return rc;
-    gather_send_kernel<<<sendGrid, 128, 0, g->sendStream>>>(G);
+    if (useTma) gather_send_tma_kernel<<<sendGrid, 32, TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK, g->sendStream>>>(G);
+    else        gather_send_kernel<<<sendGrid, 128, 0, g->sendStream>>>(G);
     g_launches++;
     TRQ_CUDA(cudaGetLastError());
     TRQ_CUDA(cudaEventRecord(g->evSent, g->sendStream));
