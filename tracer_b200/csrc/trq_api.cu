@@ -1147,6 +1147,8 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
         return (uint32_t)(v < (int)TRQ_GATHER_TILE_SHIFT_MIN ? (int)TRQ_GATHER_TILE_SHIFT_MIN : (v > 16 ? 16 : v));
     }();
     G.tileShift = tileShift;
+    static const uint32_t sendHint = [] { const char* e = getenv("TRQ_GATHER_L2_HINT"); return (uint32_t)(e ? atoi(e) : 0); }();
+    G.l2hint = sendHint;
     const uint64_t nTiles = (n + (1ull << tileShift) - 1) >> tileShift;
     // the sender starts when the caller's stream reaches this point (its counters zeroed), runs beside the trace, and the
     // caller's stream continues after both
@@ -1166,7 +1168,7 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
         const size_t need = (size_t)s->cfg[0].blocksPerSM[any ? 1 : 0][hit16 ? 1 : 0] * (s->cfg[0].smem + kSmemBlockReserve);
         size_t chosen = 228 * 1024;
         for (size_t kb : kCarveKB) if (kb * 1024 >= need) { chosen = kb * 1024; break; }
-        static const int tmaEnv = [] { const char* e = getenv("TRQ_GATHER_TMA"); return e ? atoi(e) : 0; }();
+        static const int tmaEnv = [] { const char* e = getenv("TRQ_GATHER_TMA"); return e ? atoi(e) : 1; }();
         useTma = tmaEnv != 0;
         const size_t senderSmem = useTma ? (size_t)TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK + 256 : 0;
         if (chosen - need < kSmemBlockReserve + 512 + senderSmem && chosen < 228 * 1024) {
