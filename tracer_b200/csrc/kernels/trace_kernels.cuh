@@ -654,7 +654,6 @@ struct SendParams {
     unsigned long long  n, step, timeoutNs;
     uint32_t            nPeer, unitsPerRecord;             // 2 for trq_hit, 1 for trq_hit16
     uint32_t            tileShift;
-    uint32_t            l2hint;                            // TMA sender: bulk copies carry an L2 evict_first policy
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
@@ -713,7 +712,7 @@ gather_send_kernel(const SendParams G) {
     }
 }
 
-// The same sender with the copy engine of the SM doing the work: one thread per CTA drives TMA bulk copies
+// The same sender with the copy engine of the SM doing the work (the default; TRQ_GATHER_TMA=0 selects the one above): one thread per CTA drives TMA bulk copies
 // (cp.async.bulk): tile chunk -> shared memory (completion on an mbarrier), shared memory -> the slot in every peer's
 // buffer over NVLink (bulk async-groups), two chunks in flight. No registers or LSU slots per byte in flight -- the l1tex
 // pipe the trace kernel is bound by is left alone -- and the NVLink writes are full 128-byte lines issued in long bursts.
@@ -733,10 +732,6 @@ gather_send_tma_kernel(const SendParams G) {
         const uint32_t recBytes = G.unitsPerRecord * 16u;
         uint32_t chunkNo = 0;                                             // chunks issued so far: stage = chunkNo % stages
         bool giveUp = false;
-        // the records stream through: read once here, written once over there -- first to go from either L2 (the receiver's
-        // L2 holds the tree its own trace is walking; 0.7-1.4 GB of incoming records per step would flush it)
-        unsigned long long streamPolicy;
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(streamPolicy));
         for (uint64_t tile = blockIdx.x; tile < nTiles && !giveUp; tile += gridDim.x) {
             const uint64_t first = tile << G.tileShift;
             const uint32_t count = (uint32_t)((G.n - first) < tileRecords ? (G.n - first) : tileRecords);
@@ -760,25 +755,16 @@ gather_send_tma_kernel(const SendParams G) {
                 // the peer stores that last read this stage must have read it
                 asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(TRQ_SEND_TMA_STAGES - 1) : "memory");
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(bytes) : "memory");
-                if (G.l2hint)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                                 :: "r"(sm), "l"(reinterpret_cast<const unsigned char*>(G.src) + base + off), "r"(bytes), "r"(mb), "l"(streamPolicy) : "memory");
-                else
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 :: "r"(sm), "l"(reinterpret_cast<const unsigned char*>(G.src) + base + off), "r"(bytes), "r"(mb) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(sm), "l"(reinterpret_cast<const unsigned char*>(G.src) + base + off), "r"(bytes), "r"(mb) : "memory");
                 uint32_t ready = 0;
                 while (!ready)
                     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                                  : "=r"(ready) : "r"(mb), "r"(phase) : "memory");
 #pragma unroll 1
-                for (uint32_t p = 0; p < G.nPeer; ++p) {
-                    if (G.l2hint)
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                                     :: "l"(reinterpret_cast<unsigned char*>(G.peer[p]) + base + off), "r"(sm), "r"(bytes), "l"(streamPolicy) : "memory");
-                    else
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                                     :: "l"(reinterpret_cast<unsigned char*>(G.peer[p]) + base + off), "r"(sm), "r"(bytes) : "memory");
-                }
+                for (uint32_t p = 0; p < G.nPeer; ++p)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 :: "l"(reinterpret_cast<unsigned char*>(G.peer[p]) + base + off), "r"(sm), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }

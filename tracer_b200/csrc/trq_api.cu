@@ -1147,8 +1147,6 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
         return (uint32_t)(v < (int)TRQ_GATHER_TILE_SHIFT_MIN ? (int)TRQ_GATHER_TILE_SHIFT_MIN : (v > 16 ? 16 : v));
     }();
     G.tileShift = tileShift;
-    static const uint32_t sendHint = [] { const char* e = getenv("TRQ_GATHER_L2_HINT"); return (uint32_t)(e ? atoi(e) : 0); }();
-    G.l2hint = sendHint;
     const uint64_t nTiles = (n + (1ull << tileShift) - 1) >> tileShift;
     // the sender starts when the caller's stream reaches this point (its counters zeroed), runs beside the trace, and the
     // caller's stream continues after both
