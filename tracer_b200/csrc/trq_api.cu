@@ -1167,7 +1167,9 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
         size_t chosen = 228 * 1024;
         for (size_t kb : kCarveKB) if (kb * 1024 >= need) { chosen = kb * 1024; break; }
         static const int tmaEnv = [] { const char* e = getenv("TRQ_GATHER_TMA"); return e ? atoi(e) : 1; }();
-        useTma = tmaEnv != 0;
+        // the TMA sender stages through 24 KB of shared memory; beside a trace that leaves less than that even at the largest
+        // carve-out (very deep trees) the LSU sender, which needs none, is the one that can run concurrently
+        useTma = tmaEnv != 0 && 228 * 1024 >= need + kSmemBlockReserve + 512 + (size_t)TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK + 256;
         const size_t senderSmem = useTma ? (size_t)TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK + 256 : 0;
         if (chosen - need < kSmemBlockReserve + 512 + senderSmem && chosen < 228 * 1024) {
             for (size_t kb : kCarveKB) if (kb * 1024 > chosen) { chosen = kb * 1024; break; }
