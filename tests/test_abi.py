@@ -129,3 +129,26 @@ def test_mgpu_helper_fails_loudly_without_a_gpu(built):
         d = prim.desc()
         assert lib.trq_mgpu_create(C.byref(d), None, 0, C.byref(h)) == ERR_NO_DEVICE
         assert b"no CPU fallback" in lib.trq_last_error_string()
+
+
+def test_round2_entry_points_fail_loudly_without_a_device_or_arguments(built):
+    """The device-resident entry points validate their arguments on the host and report TRQ_ERR_NO_DEVICE on a box
+    without a GPU: nothing falls back to the CPU."""
+    import torch
+    prim = H.scene_soup(20, seed=1, extent=0.2)
+    d = prim.desc()
+    h = C.c_void_p(None)
+    assert lib.trq_scene_create_device(None, 0, C.byref(h)) == ERR_INVALID
+    empty = SceneDesc()
+    assert lib.trq_scene_create_device(C.byref(empty), 0, C.byref(h)) == ERR_INVALID and b"empty bvhList" in lib.trq_last_error_string()
+    assert lib.trq_scene_update_vertices(None, None, 0, 0) == ERR_INVALID
+    assert lib.trq_bvh_build_tree_device(None, 0, 0, None, None) == ERR_INVALID
+    assert lib.trq_scene_set_kernel_config(None, 0, None) == ERR_INVALID
+    assert lib.trq_kernel_config_count() >= 2 and lib.trq_kernel_config_name(0).startswith(b"256x5")
+    assert lib.trq_kernel_config_name(99) is None
+    if not torch.cuda.is_available():
+        # host pointers are not device pointers, but the device check comes first: no GPU, no work
+        assert lib.trq_scene_create_device(C.byref(d), 0, C.byref(h)) == ERR_NO_DEVICE
+        nodes = np.zeros(2 * 20 - 1, dtype=L.bvh_dtype)
+        assert lib.trq_bvh_build_tree_device(nodes.ctypes.data, 20, 0, None, None) == ERR_NO_DEVICE
+        assert b"no CUDA device" in lib.trq_last_error_string()

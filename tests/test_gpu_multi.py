@@ -92,11 +92,16 @@ def test_peer_memory_gather_two_ranks_on_one_gpu(built, tmp_path):
     _run(tmp_path, 2, shared=True)
 
 
-def test_peer_memory_gather_one_rank_per_gpu(built, tmp_path):
+def test_peer_memory_gather_more_ranks(built, tmp_path):
+    """One rank per GPU over NCCL where the box has several GPUs (up to 4); on a one-GPU box three ranks share the device,
+    so that a world size with an odd number of peers is exercised everywhere."""
     import torch
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (the one-GPU variant above covers the protocol)")
-    _run(tmp_path, min(torch.cuda.device_count(), 4), shared=False)
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if torch.cuda.device_count() >= 2:
+        _run(tmp_path, min(torch.cuda.device_count(), 4), shared=False)
+    else:
+        _run(tmp_path, 3, shared=True)
 
 
 def test_single_process_multi_gpu_helper(built):
