@@ -255,7 +255,7 @@ int  trq_mgpu_create(const trq_scene_desc* desc, const int* devices, int nDevice
 int  trq_mgpu_device_count(const trq_mgpu* m);
 trq_scene* trq_mgpu_scene(trq_mgpu* m, int k);
 int  trq_mgpu_shard(const trq_mgpu* m, uint64_t n, int k, uint64_t* lo, uint64_t* hi);
-int  trq_mgpu_trace(trq_mgpu* m, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits);
+int  trq_mgpu_trace(trq_mgpu* m, const trq_ray* rays, uint64_t n, uint32_t flags, void* hits /* trq_hit[n], or trq_hit16[n] with TRQ_HIT16 */);
 int  trq_mgpu_destroy(trq_mgpu* m);
 
 /* ---- multi-GPU: hit gather through NVLink peer memory (one process per GPU, one node) -----------------------

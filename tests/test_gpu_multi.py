@@ -123,4 +123,7 @@ def test_single_process_multi_gpu_helper(built):
         want = one.hit(rays, any=any_hit)
         got = m.hit(rays, any=any_hit)
         assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), n
+        from tracer_b200 import layout as L
+        small = m.hit(rays, any=any_hit, hit16=True)                  # 16-byte records: shard offsets in record units
+        assert np.array_equal(small.view(np.uint8), L.pack_hit16(want).view(np.uint8)), n
     m.close(); one.close()

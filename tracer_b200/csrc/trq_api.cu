@@ -1280,16 +1280,17 @@ int trq_mgpu_shard(const trq_mgpu* m, uint64_t n, int k, uint64_t* lo, uint64_t*
     return TRQ_OK;
 }
 
-int trq_mgpu_trace(trq_mgpu* m, const trq_ray* rays, uint64_t n, uint32_t flags, trq_hit* hits) {
+int trq_mgpu_trace(trq_mgpu* m, const trq_ray* rays, uint64_t n, uint32_t flags, void* hits) {
     if (!m) return trq::fail(TRQ_ERR_INVALID, "trq_mgpu_trace: NULL handle");
     if (n == 0) return TRQ_OK;
     if (!rays || !hits) return trq::fail(TRQ_ERR_INVALID, "trq_mgpu_trace: NULL rays/hits");
+    const size_t recBytes = (flags & TRQ_HIT16) ? sizeof(trq_hit16) : sizeof(trq_hit);
     int first = TRQ_OK;
     for (int k = 0; k < (int)m->scenes.size(); ++k) {           // queue every device's range ...
         uint64_t lo, hi;
         trq_mgpu_shard(m, n, k, &lo, &hi);
         if (hi == lo) continue;
-        const int rc = trq_trace(m->scenes[k], rays + lo, hi - lo, flags | TRQ_HOST_PTRS | TRQ_HOST_ASYNC, hits + lo, nullptr);
+        const int rc = trq_trace(m->scenes[k], rays + lo, hi - lo, flags | TRQ_HOST_PTRS | TRQ_HOST_ASYNC, (uint8_t*)hits + lo * recBytes, nullptr);
         if (rc != TRQ_OK && first == TRQ_OK) first = rc;
     }
     for (trq_scene* s : m->scenes) {                            // ... then wait for all of them

@@ -332,11 +332,11 @@ class MultiGpuScene:
         check(lib.trq_mgpu_shard(self._h, n, k, C.byref(lo), C.byref(hi)), "trq_mgpu_shard")
         return lo.value, hi.value
 
-    def hit(self, rays, any=False, out=None, sort=False):
-        """numpy `ray_dtype` array -> numpy `hit_dtype` array (pinned buffers make the copies asynchronous)."""
+    def hit(self, rays, any=False, out=None, sort=False, hit16=False):
+        """numpy `ray_dtype` array -> numpy `hit_dtype` (`hit16_dtype`) array (pinned buffers make the copies asynchronous)."""
         rays = np.ascontiguousarray(rays)
-        hits = out if out is not None else np.empty(rays.size, dtype=L.hit_dtype)
-        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0)
+        hits = out if out is not None else np.empty(rays.size, dtype=L.hit16_dtype if hit16 else L.hit_dtype)
+        flags = (L.TRACE_ANY if any else 0) | (L.SORT_RAYS if sort else 0) | (L.HIT16 if hit16 else 0)
         check(lib.trq_mgpu_trace(self._h, rays.ctypes.data, rays.size, flags, hits.ctypes.data), "trq_mgpu_trace")
         return hits
 
