@@ -50,7 +50,9 @@ def main():
     ap.add_argument("--iters", type=int, default=7)
     ap.add_argument("--hit16", action="store_true")
     ap.add_argument("--cfgs", default="")
+    ap.add_argument("--tops", default="", help="comma-separated TRQ_TOP_NODES values: the scene is created once per value")
     a = ap.parse_args()
+    tops = [int(x) for x in a.tops.split(",")] if a.tops else [None]
     names = Scene.kernel_configs()
     pick = [int(x) for x in a.cfgs.split(",")] if a.cfgs else list(range(len(names)))
     for name in a.names:
@@ -60,7 +62,13 @@ def main():
             d = rays_to_torch(rays, "cuda:0")
             out = torch.empty((d.shape[0], 4 if a.hit16 else 8), dtype=torch.float32, device="cuda:0")
             base = None
-            for c in pick:
+            for top, c in [(t, c) for t in tops for c in pick]:
+                if top is not None:
+                    if not names[c].split()[1].endswith("true") and top != tops[0]:
+                        continue                                # configurations without staging: once
+                    os.environ["TRQ_TOP_NODES"] = str(top)
+                    scene.close()
+                    scene = Scene(prim, 0)
                 try:
                     staged = scene.set_kernel_config(c)
                 except Exception as e:

@@ -26,6 +26,19 @@ __global__ void __launch_bounds__(256) chase(const float4* __restrict__ tab, uin
     float acc = 0.f;
     const unsigned lane = threadIdx.x & 31u;
     float4* wbuf = sh + (threadIdx.x >> 5) * 128;   // 32 lanes x 4 quarters (MODE 3)
+    // MODE 5: every lane has the TMA unit copy its 64-byte record into its own shared-memory slot (80-byte stride: LDS.128
+    // conflict-free), one mbarrier per warp counts the 32 x 64 bytes; the lanes then read their record with four LDS.128.
+    // The global side never touches the LSU data pipe; the question is how many small bulk copies per clock an SM's TMA takes.
+    __shared__ __align__(8) unsigned long long bars[8];
+    unsigned char* tbuf = reinterpret_cast<unsigned char*>(sh) + (threadIdx.x >> 5) * (32 * 80);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[threadIdx.x >> 5]);
+    if (MODE == 5) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (int s = 0; s < steps; ++s) {
         const float4* p = tab + (size_t)idx * 4;
         float4 q0, q1, q2, q3;
@@ -33,6 +46,20 @@ __global__ void __launch_bounds__(256) chase(const float4* __restrict__ tab, uin
         else if (MODE == 1) { ldg8(p, q0, q1); ldg8(p + 2, q2, q3); }
         else if (MODE == 2) { q0 = __ldg(p); q1 = q2 = q3 = make_float4(0, 0, 0, 0); }
         else if (MODE == 4) { ldg8(p, q0, q1); q2 = q3 = make_float4(0, 0, 0, 0); }
+        else if (MODE == 5) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tbuf + lane * 80);
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(32u * 64u) : "memory");
+            __syncwarp();
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];"
+                         :: "r"(dst), "l"(p), "r"(bar) : "memory");
+            uint32_t ready = 0;
+            while (!ready)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ready) : "r"(bar), "r"((uint32_t)(s & 1)) : "memory");
+            const float4* mine = reinterpret_cast<const float4*>(tbuf + lane * 80);
+            q0 = mine[0]; q1 = mine[1]; q2 = mine[2]; q3 = mine[3];
+            __syncwarp();
+        }
         else {   // MODE 3: four lanes fetch one record (one 64-B coalesced request each), transposed through smem
             const unsigned q = lane & 3u;
 #pragma unroll
@@ -81,10 +108,10 @@ int main(int argc, char** argv) {
         float* out; CK(cudaMalloc(&out, (size_t)sms * 8 * 256 * sizeof(float)));
         const int occs[] = {2, 4, 8};                // resident 256-thread blocks per SM
         for (int occ : occs) {
-            for (int mode = 0; mode < 5; ++mode) {
+            for (int mode = 0; mode < 6; ++mode) {
                 // limit occupancy with dynamic smem: 227 KB / occ
                 int smem = (int)((200 * 1024) / occ) & ~1023;
-                if (smem < 8 * 128 * 16) smem = 8 * 128 * 16;
+                if (smem < 8 * 32 * 80) smem = 8 * 32 * 80;
                 auto launch = [&](int m) {
                     dim3 g(sms * occ), b(256);
                     switch (m) {
@@ -92,6 +119,7 @@ int main(int argc, char** argv) {
                         case 1: CK(cudaFuncSetAttribute(chase<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); chase<1><<<g, b, smem>>>(d, n, steps, out, 0); break;
                         case 2: CK(cudaFuncSetAttribute(chase<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); chase<2><<<g, b, smem>>>(d, n, steps, out, 0); break;
                         case 3: CK(cudaFuncSetAttribute(chase<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); chase<3><<<g, b, smem>>>(d, n, steps, out, 0); break;
+                        case 5: CK(cudaFuncSetAttribute(chase<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); chase<5><<<g, b, smem>>>(d, n, steps, out, 0); break;
                         case 4: CK(cudaFuncSetAttribute(chase<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); chase<4><<<g, b, smem>>>(d, n, steps, out, 0); break;
                     }
                 };
@@ -100,7 +128,7 @@ int main(int argc, char** argv) {
                 CK(cudaEventRecord(e0)); launch(mode); CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
                 float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
                 const double gathers = (double)sms * occ * 256 * steps;
-                const char* names[] = {"4xLDG128", "2xLDG256", "1xLDG128(16B)", "coop4+smem", "1xLDG256(32B)"};
+                const char* names[] = {"4xLDG128", "2xLDG256", "1xLDG128(16B)", "coop4+smem", "1xLDG256(32B)", "TMA bulk 64B -> smem"};
                 const double bytes = (mode == 2 ? 16.0 : mode == 4 ? 32.0 : 64.0);
                 printf("{\"table_MB\": %zu, \"threads_per_sm\": %d, \"mode\": \"%s\", \"ms\": %.3f, \"Ggather_s\": %.2f, \"GB_s\": %.0f}\n",
                        mb, occ * 256, names[mode], ms, gathers / ms / 1e6, gathers * bytes / ms / 1e6);
