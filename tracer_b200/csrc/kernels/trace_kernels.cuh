@@ -261,8 +261,7 @@ struct TraceParams {
     uint32_t       refillMin;      // refill when at least this many lanes of a warp are idle
     uint32_t       leafBatch;      // leave the interior phase when this many lanes wait at a leaf
     uint32_t       topCount;       // interior nodes [0, topCount) are staged in shared memory (TOP kernels), else 0
-    uint32_t       tmaFrom;        // TMAF kernels: interior nodes with index >= tmaFrom ...
-    uint32_t       tmaLanes;       // ... of the lanes in this mask are fetched by the TMA unit instead of the LSU
+    uint32_t       pad0, pad1;
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
     // trq_trace_gather: every finished record also counts towards its tile of TRQ_GATHER_TILE consecutive records
@@ -414,16 +413,7 @@ __device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src
 
 // ANY: Scene::hit(any = true). OUT: record format. BLOCK x MINB: CTA size and resident CTAs per SM.
 // TOP: the first P.topCount interior nodes are read from shared memory instead of L1/L2.
-// SSTK: far-child stack entries kept in shared memory (0 = all P.stackDepth of them); deeper entries go to a per-thread
-//       local-memory array. The stack holds one entry per ancestor whose BOTH children were hit, so deep entries are rare
-//       (C3: 99.6 % of the pushes land in the first 8); what the short stack frees pays for the staged top of the tree.
-// TMAF: a second fetch path beside the LSU. A lane's 64-byte node can be copied into the lane's own shared-memory slot by the
-//       TMA unit (cp.async.bulk, completion counted on the warp's mbarrier) and read back with four LDS.128 (80-byte slot
-//       stride: conflict-free). Those fetches never enter the L1 data pipe that bounds the kernel; the TMA unit takes one
-//       64-byte copy per ~4 clocks per SM whatever the cache hit rate (tools/gather_bench.cu, mode "TMA bulk"), so the two
-//       units share the node fetches of a warp step between them (P.tmaFrom / P.tmaLanes say which).
-#define TRQ_TMA_SLOT_WORDS 20u     // 80 bytes per lane
-template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP, int SSTK, bool TMAF>
+template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP>
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
     extern __shared__ __align__(128) uint32_t smem_u32[];
@@ -434,18 +424,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     uint32_t* const cold = smem_u32 + topWords + P.stackDepth * BLOCK + threadIdx.x; // [COLD_WORDS][BLOCK]
     float* const coldf = reinterpret_cast<float*>(cold);
     const unsigned lane = threadIdx.x & 31u;
-    constexpr int TAG = (((((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0)) * 64 + SSTK) * 2 + (TMAF ? 1 : 0);
-    // TMAF: this lane's landing slot and this warp's mbarrier
-    __shared__ __align__(8) unsigned long long tmaBars[TMAF ? BLOCK / 32 : 1];
-    uint32_t tmaPhase = 0;
-    if (TMAF) {
-        if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&tmaBars[threadIdx.x >> 5])));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
-    }
-    uint32_t spill[SSTK ? 32 - SSTK : 1];                    // stack entries SSTK.. (the reference's trail has 32 bits: depth <= 32)
+    constexpr int TAG = (((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0);
 
     if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.topSoA, P.topCount, S.topStride, &topBarrier);
 
@@ -491,13 +470,9 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
             pending = false;
         }
     };
-    auto push = [&](uint32_t ref) {
-        if (SSTK == 0 || sp < (uint32_t)SSTK) stk[sp * BLOCK] = ref; else spill[sp - (uint32_t)SSTK] = ref;
-        ++sp;
-    };
+    auto push = [&](uint32_t ref) { stk[sp * BLOCK] = ref; ++sp; };
     auto pop = [&]() {
-        if (sp == 0) cur = TRQ_REF_DONE_WORD;
-        else { --sp; cur = (SSTK == 0 || sp < (uint32_t)SSTK) ? stk[sp * BLOCK] : spill[sp - (uint32_t)SSTK]; }
+        if (sp == 0) cur = TRQ_REF_DONE_WORD; else { --sp; cur = stk[sp * BLOCK]; }
     };
     // Draws `want` queue slots for the lanes in `mask` (one atomic per warp) and returns this lane's ray index, or ~0.
     auto draw = [&](unsigned mask) -> uint64_t {
@@ -570,46 +545,10 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                       const unsigned t_ = __ballot_sync(0xffffffffu, active && TRQ_REF_KIND(cur) == REF_INTERIOR && TOP && TRQ_REF_INDEX(cur) < P.topCount);
                       if (lane == 0 && t_) atomicAdd(&g_stats[6], (unsigned long long)__popc(t_)); }
 #endif
-                    const bool onInterior = active && TRQ_REF_KIND(cur) == REF_INTERIOR;
-                    float4 q0, q1, q2, q3;
-                    if (TMAF) {
-                        // the warp's node fetches of this step, shared between the TMA unit and the LSU
+                    if (active && TRQ_REF_KIND(cur) == REF_INTERIOR) {
                         const uint32_t ni = TRQ_REF_INDEX(cur);
-                        const float4* np = S.nodes + (size_t)ni * 4u;
-                        const bool viaTma = onInterior && ni >= P.tmaFrom && ((P.tmaLanes >> lane) & 1u);
-                        // (addresses derived here, not kept in registers across the loop: the kernel is at its 48-register budget)
-                        const uint32_t tmaSlot = (uint32_t)__cvta_generic_to_shared(smem_u32 + topWords + (P.stackDepth + COLD_WORDS) * BLOCK + threadIdx.x * TRQ_TMA_SLOT_WORDS);
-                        const uint32_t tmaBar = (uint32_t)__cvta_generic_to_shared(&tmaBars[TMAF ? (threadIdx.x >> 5) : 0]);
-                        const unsigned tmask = __ballot_sync(0xffffffffu, viaTma);
-                        if (tmask) {
-                            if (lane == 0)
-                                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tmaBar), "r"(64u * (uint32_t)__popc(tmask)) : "memory");
-                            if (viaTma)
-                                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 64, [%2];"
-                                             :: "r"(tmaSlot), "l"(np), "r"(tmaBar) : "memory");
-                        }
-                        if (onInterior && !viaTma) {
-                            ldg8(np, q0, q1);
-                            ldg8(np + 2, q2, q3);
-                        }
-                        if (tmask) {
-                            uint32_t ready = 0;
-                            while (!ready)
-                                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                                             : "=r"(ready) : "r"(tmaBar), "r"(tmaPhase) : "memory");
-                            tmaPhase ^= 1u;
-                            if (viaTma)
-                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%16];\n\tld.shared.v4.f32 {%4,%5,%6,%7}, [%16+16];\n\t"
-                                             "ld.shared.v4.f32 {%8,%9,%10,%11}, [%16+32];\n\tld.shared.v4.f32 {%12,%13,%14,%15}, [%16+48];"
-                                             : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w),
-                                               "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w)
-                                             : "r"(tmaSlot) : "memory");
-                        }
-                    }
-                    if (onInterior) {
-                        const uint32_t ni = TRQ_REF_INDEX(cur);
-                        if (TMAF) {
-                        } else if (TOP && ni < P.topCount) {                  // top of the tree: four LDS.128 from this CTA's copy
+                        float4 q0, q1, q2, q3;
+                        if (TOP && ni < P.topCount) {                         // top of the tree: four LDS.128 from this CTA's copy
                             const float4* tp = topNodes + ni;
                             q0 = tp[0]; q1 = tp[P.topCount]; q2 = tp[2u * P.topCount]; q3 = tp[3u * P.topCount];
                         } else {

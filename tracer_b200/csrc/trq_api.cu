@@ -85,20 +85,17 @@ constexpr size_t kSmemDynamicMax = kSmemPerBlockMax - 1024u;   // dynamic part: 
 struct KernelCfg {
     int block, minb;
     bool top;
-    int sstk;                     // far-child stack entries per lane in shared memory (0 = scene depth + 1); deeper ones in local memory
-    bool tma;                     // TMA unit as a second node-fetch path (an 80-byte landing slot per lane)
     const void* fn[2][2];
     const char* name;
 };
-#define TRQ_CFG(B, M, T, K, X)                                                                                \
-    { B, M, T, K, X,                                                                                          \
-      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T, K, X>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T, K, X> }, \
-        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T, K, X>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T, K, X> } }, \
-      #B "x" #M " top=" #T " sstk=" #K " tma=" #X }
+#define TRQ_CFG(B, M, T)                                                                                      \
+    { B, M, T,                                                                                                \
+      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T> }, \
+        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T> } }, \
+      #B "x" #M " top=" #T }
 const KernelCfg kCfgs[] = {
-    TRQ_CFG(256, 5, false, 0, false),     // 0: five CTAs of 256 threads per SM, every node from L1 / L2 (large scenes)
-    TRQ_CFG(1024, 1, true, 0, false),     // 1: one CTA of 1024 threads per SM sharing one TMA-staged copy of the top levels (small trees)
-    TRQ_CFG(256, 5, false, 8, true),      // 2: cfg 0's shape, 8-entry shared-memory stack, node fetches shared between the LSU and the TMA unit
+    TRQ_CFG(256, 5, false),       // 0: five CTAs of 256 threads per SM, every node from L1 / L2 (large scenes)
+    TRQ_CFG(1024, 1, true),       // 1: one CTA of 1024 threads per SM sharing one TMA-staged copy of the top levels (small trees)
 #ifdef TRQ_EXTRA_CFGS
     TRQ_EXTRA_CFGS
 #endif
@@ -151,13 +148,6 @@ struct trq_scene {
     cudaStream_t stageStream[kStageBufs] = {};   // one stream per staging buffer: copy in, trace, copy out in stream order
     bool stageReady = false;
     uint64_t stageSeq = 0;        // chunks ever staged (ring position)
-    // direct host path (pinned host buffers): the trace reads the rays straight from host memory and a TMA sender ships
-    // finished tiles of records straight into the host buffer -- one trace launch per call, no chunking
-    uint8_t* d_directHits = nullptr; size_t directCap = 0;
-    uint32_t* d_directTiles = nullptr; size_t directTiles = 0;     // + 8 trailing words: blocksDone, dummy flag / count
-    cudaStream_t directSend = nullptr;
-    cudaEvent_t evDirectStart = nullptr, evDirectSent = nullptr;
-    unsigned int* h_directStatus = nullptr; unsigned int* d_directStatus = nullptr;
     // optional per-kernel timing (trq_profile_enable): events around the trace and resolve kernels
     std::mutex profMutex;
     bool profile = false;
@@ -190,11 +180,6 @@ void free_scene(trq_scene* s) {
         cudaFree(s->d_stageRays[b]); cudaFree(s->d_stageHits[b]);
         if (s->stageStream[b]) cudaStreamDestroy(s->stageStream[b]);
     }
-    pool_free(s->d_directHits); pool_free(s->d_directTiles);
-    if (s->directSend) cudaStreamDestroy(s->directSend);
-    if (s->evDirectStart) cudaEventDestroy(s->evDirectStart);
-    if (s->evDirectSent) cudaEventDestroy(s->evDirectSent);
-    if (s->h_directStatus) cudaFreeHost(s->h_directStatus);
     for (int k = 0; k < kProfRing; ++k)
         for (int j = 0; j < 3; ++j) if (s->evProf[k][j]) cudaEventDestroy(s->evProf[k][j]);
     delete s;
@@ -373,11 +358,6 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         P.queue = s->d_queues + (s->queueNext.fetch_add(1) % kQueueRing);
         P.stackDepth = cs.stackDepth; P.refillMin = refillMin; P.leafBatch = leafBatch;
         P.topCount = K.top ? cs.topCount : 0;
-        {   // which node fetches go through the TMA unit (cfg with tma=true): nodes from this index on, for the lanes of this mask
-            const char* f = getenv("TRQ_TMA_FROM"); const char* m = getenv("TRQ_TMA_LANES");
-            P.tmaFrom = f ? (uint32_t)strtoul(f, nullptr, 0) : 0u;
-            P.tmaLanes = m ? (uint32_t)strtoul(m, nullptr, 0) : 0xaaaaaaaau;
-        }
         P.order = nullptr; P.nPtr = nPtr;
         P.tileDone = tileDone; P.tileShift = tileShift;
         // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
@@ -459,107 +439,6 @@ int ensure_staging(trq_scene* s, uint64_t chunk) {
     return TRQ_OK;
 }
 
-// The sender CTA of trq_trace_gather / the direct host path must fit beside the resident trace CTAs. The driver sizes the SM's
-// shared-memory carve-out to what the trace needs, rounded up to a supported size; when that leaves less than the sender
-// needs (C3's depth: 5 x 39 KB = 195 of 196 KB), ask for the next size for the coming launch. Returns the kernel whose
-// attribute was changed (restore it with restore_carveout after the launch), or NULL; *useTma: whether the TMA sender fits.
-const void* bump_carveout_for_sender(trq_scene* s, uint32_t flags, bool* useTma) {
-    static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
-    static const int tmaEnv = [] { const char* e = getenv("TRQ_GATHER_TMA"); return e ? atoi(e) : 1; }();
-    const bool any = (flags & TRQ_TRACE_ANY) != 0, hit16 = (flags & TRQ_HIT16) != 0;
-    const void* fn = kCfgs[0].fn[any ? 1 : 0][hit16 ? 1 : 0];
-    const size_t need = (size_t)s->cfg[0].blocksPerSM[any ? 1 : 0][hit16 ? 1 : 0] * (s->cfg[0].smem + kSmemBlockReserve);
-    // the TMA sender stages through 24 KB of shared memory; beside a trace that leaves less than that even at the largest
-    // carve-out (very deep trees) the LSU sender, which needs none, is the one that can run concurrently
-    const size_t tmaSmem = (size_t)TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK + 256;
-    *useTma = tmaEnv != 0 && 228 * 1024 >= need + kSmemBlockReserve + 512 + tmaSmem;
-    const size_t senderSmem = *useTma ? tmaSmem : 0;
-    size_t chosen = 228 * 1024;
-    for (size_t kb : kCarveKB) if (kb * 1024 >= need) { chosen = kb * 1024; break; }
-    if (chosen - need < kSmemBlockReserve + 512 + senderSmem && chosen < 228 * 1024) {
-        for (size_t kb : kCarveKB) if (kb * 1024 >= need + kSmemBlockReserve + 512 + senderSmem) { chosen = kb * 1024; break; }
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((chosen * 100 + kSmemPerSM - 1) / kSmemPerSM)) == cudaSuccess) return fn;
-        cudaGetLastError();
-    }
-    return nullptr;
-}
-void restore_carveout(const void* fn) {
-    if (fn) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
-}
-
-// log2 of the records per gather tile: small tiles follow the trace closely, large ones cost fewer polls (flat 2^9 .. 2^13)
-uint32_t gather_tile_shift() {
-    static const uint32_t shift = [] {
-        const char* e = getenv("TRQ_GATHER_TILE_SHIFT");
-        int v = e ? atoi(e) : 11;
-        return (uint32_t)(v < (int)TRQ_GATHER_TILE_SHIFT_MIN ? (int)TRQ_GATHER_TILE_SHIFT_MIN : (v > 16 ? 16 : v));
-    }();
-    return shift;
-}
-
-// Direct host path: both host buffers are pinned (device-accessible). ONE trace launch reads the rays straight from host
-// memory (zero-copy 256-bit loads at refill: 16 consecutive rays = 512 contiguous bytes per warp) and writes its records to a
-// device buffer; the TMA sender of trq_trace_gather, with the HOST buffer as its only "peer", ships finished tiles back over
-// PCIe while the trace runs. No chunk pipeline: no per-chunk launch tails, both directions of the link busy from the first
-// ray to the last.
-int trace_host_direct(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags, void* d_hitsHost) {
-    const size_t recBytes = (flags & TRQ_HIT16) ? sizeof(trq_hit16) : sizeof(trq_hit);
-    std::lock_guard<std::mutex> lock(s->stageMutex);
-    int rc = ensure_staging(s, 1);                            // the streams
-    if (rc != TRQ_OK) return rc;
-    cudaStream_t st = s->stageStream[0];
-    if (!s->directSend) {
-        TRQ_CUDA(cudaStreamCreateWithFlags(&s->directSend, cudaStreamNonBlocking));
-        TRQ_CUDA(cudaEventCreateWithFlags(&s->evDirectStart, cudaEventDisableTiming));
-        TRQ_CUDA(cudaEventCreateWithFlags(&s->evDirectSent, cudaEventDisableTiming));
-        TRQ_CUDA(cudaHostAlloc((void**)&s->h_directStatus, sizeof(unsigned int), cudaHostAllocMapped));
-        *s->h_directStatus = 0;
-        TRQ_CUDA(cudaHostGetDevicePointer((void**)&s->d_directStatus, s->h_directStatus, 0));
-    }
-    const uint32_t shift = gather_tile_shift();
-    const uint64_t nTiles = (n + (1ull << shift) - 1) >> shift;
-    const uint64_t tilesAlloc = (nTiles + 1) & ~1ull;          // the 64-bit words behind the counters stay 8-byte aligned
-    if (n * recBytes > s->directCap || tilesAlloc > s->directTiles) {
-        TRQ_CUDA(cudaStreamSynchronize(st)); TRQ_CUDA(cudaStreamSynchronize(s->directSend));
-        pool_free(s->d_directHits); pool_free(s->d_directTiles);
-        s->d_directHits = nullptr; s->d_directTiles = nullptr; s->directCap = 0; s->directTiles = 0;
-        TRQ_CUDA(pool_malloc((void**)&s->d_directHits, n * recBytes));
-        TRQ_CUDA(pool_malloc((void**)&s->d_directTiles, (tilesAlloc + 8) * sizeof(uint32_t)));
-        TRQ_CUDA(cudaDeviceSynchronize());                    // pool memory handed out on the legacy stream, used on others
-        s->directCap = n * recBytes; s->directTiles = tilesAlloc;
-    }
-    uint32_t* tail = s->d_directTiles + s->directTiles;       // [0] blocksDone, [2..3] flag, [4..5] count
-    SendParams G{};
-    G.src = (const uint4*)s->d_directHits;
-    G.n = n; G.step = 1; G.timeoutNs = 10ull * 1000000000ull;
-    G.unitsPerRecord = (flags & TRQ_HIT16) ? 1u : 2u;
-    G.tileShift = shift;
-    G.tileDone = s->d_directTiles; G.blocksDone = tail; G.status = s->d_directStatus;
-    G.ownFlag = (unsigned long long*)(tail + 2); G.ownCount = (unsigned long long*)(tail + 4);
-    G.nPeer = 1; G.peer[0] = (uint4*)d_hitsHost;
-    G.peerFlag[0] = G.ownFlag; G.peerCount[0] = G.ownCount;
-    TRQ_CUDA(cudaMemsetAsync(s->d_directTiles, 0, (s->directTiles + 8) * sizeof(uint32_t), st));
-    TRQ_CUDA(cudaEventRecord(s->evDirectStart, st));
-    TRQ_CUDA(cudaStreamWaitEvent(s->directSend, s->evDirectStart, 0));
-    bool useTma = false;
-    const void* bumped = bump_carveout_for_sender(s, flags, &useTma);
-    rc = launch_trace(s, d_rays, n, flags, s->d_directHits, st, nullptr, s->d_directTiles, shift);
-    restore_carveout(bumped);
-    if (rc != TRQ_OK) return rc;
-    unsigned sendGrid = (unsigned)s->numSMs;
-    if (nTiles < sendGrid) sendGrid = (unsigned)nTiles;
-    if (useTma) gather_send_tma_kernel<<<sendGrid, 32, TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK, s->directSend>>>(G);
-    else        gather_send_kernel<<<sendGrid, 128, 0, s->directSend>>>(G);
-    g_launches++;
-    TRQ_CUDA(cudaGetLastError());
-    TRQ_CUDA(cudaEventRecord(s->evDirectSent, s->directSend));
-    TRQ_CUDA(cudaStreamWaitEvent(st, s->evDirectSent, 0));
-    if (flags & TRQ_HOST_ASYNC) return TRQ_OK;
-    TRQ_CUDA(cudaStreamSynchronize(st));
-    if (*(volatile unsigned int*)s->h_directStatus) return trq::fail(TRQ_ERR_CUDA, "trq_trace: the record sender timed out");
-    return TRQ_OK;
-}
-
 // Host-pointer path: the batch is cut into chunks; chunk k goes through staging buffer k % kStageBufs on that
 // buffer's own stream (copy in, trace, copy out, in stream order). Different chunks overlap on the two copy engines
 // and the SMs, buffer reuse is ordered by the stream itself, and a chunk costs four driver calls.
@@ -573,16 +452,6 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, vo
         return (uint64_t)(v < 1024 ? 1024 : v);
     }();
     const size_t recBytes = (flags & TRQ_HIT16) ? sizeof(trq_hit16) : sizeof(trq_hit);
-    static const int directEnv = [] { const char* e = getenv("TRQ_HOST_DIRECT"); return e ? atoi(e) : 0; }();
-    if (directEnv && n >= 65536 && n <= (1ull << 31) && !(flags & (TRQ_SORT_RAYS | TRQ_KERNEL_REFLAYOUT))) {
-        // both buffers pinned and mapped into the device's address space?
-        cudaPointerAttributes ar{}, ah{};
-        if (cudaPointerGetAttributes(&ar, rays) == cudaSuccess && cudaPointerGetAttributes(&ah, hits) == cudaSuccess &&
-            ar.type == cudaMemoryTypeHost && ah.type == cudaMemoryTypeHost && ar.devicePointer && ah.devicePointer &&
-            !(((uintptr_t)ar.devicePointer) & 31u) && !(((uintptr_t)ah.devicePointer) & 15u))
-            return trace_host_direct(s, (const trq_ray*)ar.devicePointer, n, flags, ah.devicePointer);
-        cudaGetLastError();
-    }
     std::lock_guard<std::mutex> lock(s->stageMutex);
     // a sorted chunk is only as coherent as it is large: C5 e2e 461 / 605 / 599 / 504 Mrays/s at 512K / 1M / 2M / 4M rays
     const uint64_t want = (flags & TRQ_SORT_RAYS) ? 2 * chunkRays : chunkRays;
@@ -711,9 +580,8 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
     for (int c = 0; c < kNumCfgs; ++c) {
         const KernelCfg& K = kCfgs[c];
         trq_scene::CfgState& cs = s->cfg[c];
-        // short-stack configurations keep K.sstk levels in shared memory; deeper ones spill to local memory (depth <= 32 in all)
-        cs.stackDepth = K.sstk ? (uint32_t)K.sstk : s->stackDepth;
-        const size_t perRay = ((size_t)cs.stackDepth + COLD_WORDS + (K.tma ? TRQ_TMA_SLOT_WORDS : 0u)) * K.block * sizeof(uint32_t);
+        cs.stackDepth = s->stackDepth;
+        const size_t perRay = ((size_t)cs.stackDepth + COLD_WORDS) * K.block * sizeof(uint32_t);
         size_t budget = kSmemPerSM / (size_t)K.minb - kSmemBlockReserve;
         if (budget > kSmemDynamicMax) budget = kSmemDynamicMax;
         cs.topCount = 0;
@@ -731,12 +599,6 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
         for (int a = 0; a < 2 && e == cudaSuccess; ++a)
             for (int f = 0; f < 2 && e == cudaSuccess; ++f) {
                 if (cs.smem > 48 * 1024) e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDynamicMax);
-                if (e == cudaSuccess && K.sstk) {
-                    // carve out only what the resident CTAs need: the rest of the SM's 256 KB stays L1 cache, which holds the
-                    // lines of every request in flight (a 28 KB L1 costs the 1 M soup 40 %, profiles/r02_l1_l2_experiments.txt)
-                    int pct = (int)(((cs.smem + kSmemBlockReserve) * (size_t)K.minb * 100 + kSmemPerSM - 1) / kSmemPerSM);
-                    e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-                }
                 if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs.blocksPerSM[a][f], K.fn[a][f], K.block, cs.smem);
                 if (e == cudaSuccess && cs.blocksPerSM[a][f] < 1) cs.usable = false;
             }
@@ -1279,7 +1141,12 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
         G.peerFlag[k] = (unsigned long long*)g->peerBase[r] + g->rank;
         G.peerCount[k] = (unsigned long long*)(g->peerBase[r] + kGatherCountsAt) + phase * TRQ_GATHER_MAX_RANKS + g->rank;
     }
-    const uint32_t tileShift = gather_tile_shift();
+    // records per tile: small tiles follow the trace closely (short tail after its last ray), large ones cost fewer polls
+    static const uint32_t tileShift = [] {
+        const char* e = getenv("TRQ_GATHER_TILE_SHIFT");
+        int v = e ? atoi(e) : 11;
+        return (uint32_t)(v < (int)TRQ_GATHER_TILE_SHIFT_MIN ? (int)TRQ_GATHER_TILE_SHIFT_MIN : (v > 16 ? 16 : v));
+    }();
     G.tileShift = tileShift;
     const uint64_t nTiles = (n + (1ull << tileShift) - 1) >> tileShift;
     // the sender starts when the caller's stream reaches this point (its counters zeroed), runs beside the trace, and the
@@ -1289,10 +1156,29 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
     TRQ_CUDA(cudaStreamWaitEvent(g->sendStream, g->evStart, 0));
     unsigned sendGrid = (unsigned)g->numSMs;
     if (nTiles < sendGrid) sendGrid = nTiles ? (unsigned)nTiles : 1u;
-    bool useTma = false;
-    const void* bumped = n ? bump_carveout_for_sender(s, flags, &useTma) : nullptr;
+    // The sender CTA (no shared memory of its own, 1 KB of per-CTA reserve) must fit beside the resident trace CTAs. The
+    // driver sizes the SM's shared-memory carve-out to what the trace needs, rounded up to a supported size; when that leaves
+    // less than the reserve (C3's depth: 5 x 39 KB = 195 of 196 KB), ask for the next size for this launch.
+    const bool any = (flags & TRQ_TRACE_ANY) != 0, hit16 = (flags & TRQ_HIT16) != 0;
+    const void* fn = kCfgs[0].fn[any ? 1 : 0][hit16 ? 1 : 0];
+    bool bumped = false, useTma = false;
+    if (n) {
+        static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+        const size_t need = (size_t)s->cfg[0].blocksPerSM[any ? 1 : 0][hit16 ? 1 : 0] * (s->cfg[0].smem + kSmemBlockReserve);
+        size_t chosen = 228 * 1024;
+        for (size_t kb : kCarveKB) if (kb * 1024 >= need) { chosen = kb * 1024; break; }
+        static const int tmaEnv = [] { const char* e = getenv("TRQ_GATHER_TMA"); return e ? atoi(e) : 1; }();
+        // the TMA sender stages through 24 KB of shared memory; beside a trace that leaves less than that even at the largest
+        // carve-out (very deep trees) the LSU sender, which needs none, is the one that can run concurrently
+        useTma = tmaEnv != 0 && 228 * 1024 >= need + kSmemBlockReserve + 512 + (size_t)TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK + 256;
+        const size_t senderSmem = useTma ? (size_t)TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK + 256 : 0;
+        if (chosen - need < kSmemBlockReserve + 512 + senderSmem && chosen < 228 * 1024) {
+            for (size_t kb : kCarveKB) if (kb * 1024 > chosen) { chosen = kb * 1024; break; }
+            bumped = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((chosen * 100 + kSmemPerSM - 1) / kSmemPerSM)) == cudaSuccess;
+        }
+    }
     const int rc = launch_trace(s, rays, n, flags, own, st, nullptr, g->d_tileDone, tileShift);     // first: its CTAs take their places
-    restore_carveout(bumped);
+    if (bumped) cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
     if (rc != TRQ_OK) return rc;
     if (useTma) gather_send_tma_kernel<<<sendGrid, 32, TRQ_SEND_TMA_STAGES * TRQ_SEND_TMA_CHUNK, g->sendStream>>>(G);
     else        gather_send_kernel<<<sendGrid, 128, 0, g->sendStream>>>(G);
