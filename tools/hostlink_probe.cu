@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
@@ -58,6 +59,14 @@ __global__ void __launch_bounds__(32) tma_copy(const unsigned char* __restrict__
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// stand-in for the trace of one chunk: streams the chunk from `in` to `out` `reps` times (reps sets how long it occupies the SMs)
+__global__ void __launch_bounds__(256) chunk_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t nUnits, int reps) {
+    for (int r = 0; r < reps; ++r)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nUnits; i += (size_t)gridDim.x * blockDim.x) {
+            uint4 v = in[i]; v.x += (uint32_t)r; out[i] = v;
+        }
 }
 
 int main(int argc, char** argv) {
@@ -111,5 +120,29 @@ int main(int argc, char** argv) {
     timeit("zc_read32x5 + tma_write", [&] { zc_read<<<sms * 5, 256, 0, s0>>>((const uint4*)dIn, (uint4*)dA, bytes / 32, 32); }, [&] { tma_copy<<<sms, 32, smemT, s1>>>(dB, dOut, bytes); }, true);
     timeit("ce_h2d + tma_write", [&] { CK(cudaMemcpyAsync(dA, hIn, bytes, cudaMemcpyHostToDevice, s0)); }, [&] { tma_copy<<<sms, 32, smemT, s1>>>(dB, dOut, bytes); }, true);
     timeit("tma_read + ce_d2h", [&] { tma_copy<<<sms, 32, smemT, s0>>>(dIn, dA, bytes); }, [&] { CK(cudaMemcpyAsync(hOut, dB, bytes, cudaMemcpyDeviceToHost, s1)); }, true);
+    // the chunk pipeline of trq_trace(TRQ_HOST_PTRS): chunk k on stream k % S: H2D, kernel, D2H in stream order
+    cudaStream_t ps[8]; for (int k = 0; k < 8; ++k) CK(cudaStreamCreateWithFlags(&ps[k], cudaStreamNonBlocking));
+    cudaEvent_t p0, p1; CK(cudaEventCreate(&p0)); CK(cudaEventCreate(&p1));
+    cudaEvent_t done[8]; for (int k = 0; k < 8; ++k) CK(cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+    for (int reps : {0, 8}) for (int S : {2, 3, 4, 8}) for (size_t chunkMB : {2, 4, 8, 16, 32}) {
+        const size_t chunk = chunkMB << 20;
+        float best = 1e9f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaDeviceSynchronize());
+            const auto t0 = std::chrono::steady_clock::now();
+            int k = 0;
+            for (size_t off = 0; off < bytes; off += chunk, ++k) {
+                const size_t len = (bytes - off) < chunk ? (bytes - off) : chunk;
+                cudaStream_t st = ps[k % S];
+                CK(cudaMemcpyAsync(dA + off, hIn + off, len, cudaMemcpyHostToDevice, st));
+                if (reps) chunk_kernel<<<sms * 4, 256, 0, st>>>((const uint4*)(dA + off), (uint4*)(dB + off), len / 16, reps);
+                CK(cudaMemcpyAsync(hOut + off, dB + off, len, cudaMemcpyDeviceToHost, st));
+            }
+            CK(cudaDeviceSynchronize());
+            const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (rep > 0 && ms < best) best = ms;
+        }
+        printf("pipeline %2zu MB chunks, %d streams, kernel x%d   %7.3f ms wall  %6.1f GB/s per direction\n", chunkMB, S, reps, best, bytes / best / 1e6);
+    }
     return 0;
 }
