@@ -92,3 +92,51 @@ def test_host_threads_share_one_scene(built):
     assert 0 < n <= 64 and a > 0
     scene.profile(False)
     scene.close()
+
+
+def test_wavefront_step_is_cuda_graph_capturable(built):
+    """cast -> trace -> spawn -> trace_indirect issue nothing but kernels and stream-ordered allocations, so a whole
+    wavefront step can be captured once and replayed (the reference re-encodes its command buffer every frame,
+    AAPLRenderer.mm:712-720). Replays give the eager results bit for bit; any-hit and TRQ_SORT_RAYS launches capture too."""
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H, rays_to_torch
+    prim = H.scene_c2()
+    scene = Scene(prim, 0)
+    W, Hh = 320, 180
+    cam = ((278, 278, -800), (278, 278, 278), (0, 1, 0), np.float32(45 * (np.pi / 180)))
+    dev = "cuda:0"
+    r0 = torch.empty((W * Hh, 8), dtype=torch.float32, device=dev); h0 = torch.empty_like(r0)
+    r1 = torch.empty_like(r0); h1 = torch.zeros_like(r0); ha = torch.empty_like(r0)
+    s1 = torch.empty(W * Hh, dtype=torch.int32, device=dev); c1 = torch.zeros(1, dtype=torch.int64, device=dev)
+    big = rays_to_torch(H.random_rays(70000, seed=8, lo=(0, 0, 0), hi=(555, 555, 555)), dev); hs = torch.empty_like(big)
+
+    def step():
+        scene.cast_rays(*cam, W, Hh, out=r0)
+        scene.hit(r0, out=h0)
+        scene.spawn_bounce(r0, h0, seed_base=7, out=r1, src=s1, count=c1)
+        scene.hit_indirect(r1, c1, out=h1)
+        scene.hit(r0, any=True, out=ha)
+        scene.hit(big, out=hs, sort=True)
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.synchronize()
+    n1 = int(c1.item())
+    assert 0 < n1 <= W * Hh
+    # the bounce wave is compacted with one atomic per warp: its order varies from run to run, its content does not
+    def canon():
+        k = torch.argsort(s1[:n1].to(torch.int64))
+        return [h0.clone(), h1[:n1][k].clone(), ha.clone(), hs.clone(), c1.clone()]
+    want = canon()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        step()
+    for rep in range(3):
+        for t in (h0, h1, ha, hs):
+            t.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(want, canon()):
+            assert torch.equal(a.view(torch.int32) if a.dtype == torch.float32 else a, b.view(torch.int32) if b.dtype == torch.float32 else b), rep
+    scene.close()
