@@ -180,3 +180,52 @@ def test_device_wavefront_triangle_only_scene(built, port):
         for k in ("t", "u", "v"):
             assert np.array_equal(bits(got[k]), bits(want[k])), k
     scene.close()
+
+
+def test_cube_with_a_down_scaling_model_matrix(built, port):
+    """Cube::hit_test hands the CALLER's range.y to its local-space box test (Cube.hh:25, AABB.hh:116-145). When the model
+    matrix scales down, a ray that starts inside the cube with range.y below the local exit distance is accepted at local
+    t = range.y with axisPick = 0 -- an outcome that running the test again with another range.y does not reproduce (half of
+    the hits below). trq_trace sees the real range; trq_expand_hits and the spawns rebuild those records from (t, u, v)
+    (intersect.cuh: cube_surface). All three must give the oracle's records bit for bit."""
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H, hits_to_numpy, rays_to_torch
+    model = H.translation4x4(0.5, -0.25, 2.0) @ H.rotation4x4(0.3, (0, 1, 0)) @ H.scale4x4(0.01, 0.02, 0.015)
+    c = H.make_cube(model, 3)
+    c["box_mini"], c["box_maxi"] = (-100, -60, -80), (100, 60, 80)
+    prim = H.build_primitive(cubes=np.array([c, H.cornell_cubes()[0]], dtype=L.cube_dtype))
+    rng = np.random.default_rng(5)
+    n = 20000
+    rays = np.zeros(n, dtype=L.ray_dtype)
+    local = rng.uniform([-95, -55, -75], [95, 55, 75], size=(n, 3))
+    M = model.astype(np.float64)
+    rays["o"] = ((M[:3, :3] @ local.T).T + M[:3, 3]).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tmax"] = rng.uniform(0.5, 150.0, size=n).astype(np.float32)
+    want = port.trace(prim, rays, records=True, nthreads=8)
+    unclipped = rays.copy(); unclipped["tmax"] = L.FLT_MAX
+    other = port.trace(prim, unclipped, records=True, nthreads=8)["records"]
+    m = want["records"]["hit"] == 1
+    clipped = m & ~np.all(bits(want["records"]["p"]) == bits(other["p"]), axis=1)
+    assert clipped.sum() > n // 4, "the case under test must actually occur"
+
+    scene = Scene(prim, 0)
+    dr = rays_to_torch(rays, "cuda:0")
+    dh = scene.hit(dr)
+    hits = hits_to_numpy(dh)
+    for k in want["hits"].dtype.names:
+        assert np.array_equal(bits(hits[k]), bits(want["hits"][k])), k
+    recs = scene.expand(dr, dh).cpu().numpy().view(L.record_dtype).reshape(-1)
+    assert np.array_equal(recs["hit"], want["records"]["hit"])
+    for k in ("t", "p", "gn", "sn", "uv", "front", "material"):
+        assert np.array_equal(bits(recs[k][m]), bits(want["records"][k][m])), k
+    out, src, cnt = scene.spawn_bounce(dr, dh, seed_base=3)
+    wrays, wsrc = H.bounce_rays(want["records"], seed_base=3)
+    k = int(cnt.item())
+    assert k == wrays.size
+    order = np.argsort(src.cpu().numpy()[:k].astype(np.uint32), kind="stable")
+    got = _np_rays(out, k)[order]
+    assert np.array_equal(src.cpu().numpy()[:k].astype(np.uint32)[order], wsrc)
+    assert np.array_equal(bits(got["o"]), bits(wrays["o"]))
+    scene.close()

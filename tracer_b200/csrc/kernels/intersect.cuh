@@ -256,4 +256,27 @@ __device__ __forceinline__ bool cube_hit(const RefCube* __restrict__ cb, const R
     return true;
 }
 
+// The HitRecord fields of a cube hit the query has already found (trq_hit: t, u, v). Cube::hit_test's local box test starts
+// its exit search at the CALLER's range.y (AABB.hh:116-145), which trq_hit does not carry, so the test cannot simply be run
+// again. It does not have to be: re-running it with range.y = FLT_MAX gives the original outcome unless the ray started inside
+// the local box and the original range.y was <= every exit distance (possible when the model matrix scales DOWN: local
+// distances are longer than world distances). In that case the original kept axisPick = 0 and local t = range.y, so its
+// local hit point was (the x plane the ray leaves through, uv.x, uv.y) and its normal +-x: everything follows from (u, v).
+// The two cases are told apart by (t, u, v), which the re-run reproduces bit for bit in the first case.
+__device__ __forceinline__ void cube_surface(const RefCube* __restrict__ cb, const RayCtx& r, float ht, float hu, float hv, Surface& s) {
+    float t = 0.0f;
+    Surface a;
+    if (cube_hit(cb, r, FLT_MIN, FLT_MAX, t, &a) && __float_as_uint(t) == __float_as_uint(ht) &&
+        __float_as_uint(a.uvx) == __float_as_uint(hu) && __float_as_uint(a.uvy) == __float_as_uint(hv)) { s = a; return; }
+    const f3 ld = normalize3(m4_mul3(cb->inverse, r.d, 0.0f));                       // Cube.hh:20-23
+    const bool pos = ld.x > 0.0f;
+    const f3 lp = make_f3(pos ? cb->box.maxi[0] : cb->box.mini[0], hu, hv);          // AABB.hh:147-157 with axisPick = 0
+    const f3 lgn = make_f3(pos ? 1.0f : -1.0f, 0.0f, 0.0f);
+    s.gn = normalize3(m4_mul3(cb->normal, lgn, 0.0f));                               // Cube.hh:41-42
+    finish_surface(r, s);
+    s.p = m4_mul3(cb->model, lp, 1.0f);                                              // Cube.hh:26-27
+    s.uvx = hu; s.uvy = hv;
+    s.material = cb->material;
+}
+
 }  // namespace trq

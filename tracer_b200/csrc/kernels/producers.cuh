@@ -121,7 +121,7 @@ __device__ __forceinline__ bool surface_of_hit(const SceneDev& S, const trq_ray*
     if (pType == TRQ_TRIANGLE)     tri_surface(S.verts, S.idx, pIndex, h1.x, h1.y, ray, s);
     else if (pType == TRQ_SPHERE)  sphere_surface(&S.spheres[pIndex], h0.x, ray, s);
     else if (pType == TRQ_SQUARE)  square_hit(&S.squares[pIndex], ray, h0.x, h0.x, t, &s);
-    else if (pType == TRQ_CUBE)    cube_hit(&S.cubes[pIndex], ray, FLT_MIN, FLT_MAX, t, &s);
+    else if (pType == TRQ_CUBE)    cube_surface(&S.cubes[pIndex], ray, h0.x, h1.x, h1.y, s);
     return true;
 }
 

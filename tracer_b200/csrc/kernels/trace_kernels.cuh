@@ -879,7 +879,7 @@ expand_hits_kernel(SceneDev S, const trq_ray* __restrict__ rays, const trq_hit* 
         if (h.pType == TRQ_TRIANGLE)     tri_surface(S.verts, S.idx, h.pIndex, h.u, h.v, ray, s);
         else if (h.pType == TRQ_SPHERE)  sphere_surface(&S.spheres[h.pIndex], h.t, ray, s);
         else if (h.pType == TRQ_SQUARE)  square_hit(&S.squares[h.pIndex], ray, h.t, h.t, t, &s);
-        else if (h.pType == TRQ_CUBE)    cube_hit(&S.cubes[h.pIndex], ray, FLT_MIN, FLT_MAX, t, &s);
+        else if (h.pType == TRQ_CUBE)    cube_surface(&S.cubes[h.pIndex], ray, h.t, h.u, h.v, s);
         out.hit = 1; out.t = h.t;
         out.p[0] = s.p.x; out.p[1] = s.p.y; out.p[2] = s.p.z;
         out.gn[0] = s.gn.x; out.gn[1] = s.gn.y; out.gn[2] = s.gn.z;
