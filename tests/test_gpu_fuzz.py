@@ -72,6 +72,17 @@ def scenes(rng):
     yield "lattice", H.build_primitive(tri, idx)
     sph = np.array([H.make_sphere(float(rng.uniform(0.2, 1.5)), rng.uniform(-3, 3, 3), i) for i in range(60)], dtype=L.sphere_dtype)
     yield "spheres", H.build_primitive(spheres=sph)
+    # cubes whose model matrices scale down / up / shear-free rotate, spheres and squares around them: the leaf types whose
+    # records the packed kernel finishes out of line
+    cubes = []
+    for i in range(6):
+        sc = rng.uniform(0.01, 0.05, 3) if i % 2 == 0 else rng.uniform(0.5, 2.0, 3)
+        m = H.translation4x4(*rng.uniform(-3, 3, 3)) @ H.rotation4x4(float(rng.uniform(0, 3)), (0, 1, 0)) @ H.scale4x4(*sc)
+        c = H.make_cube(m, i)
+        if i % 2 == 0:
+            c["box_mini"], c["box_maxi"] = (-50, -40, -30), (50, 40, 30)
+        cubes.append(c)
+    yield "cubes", H.build_primitive(cubes=np.array(cubes, dtype=L.cube_dtype), spheres=sph[:10])
 
 
 def _seeds():
@@ -83,17 +94,55 @@ def _seeds():
     return [1, 2, 3]
 
 
+def _assert_records(scene, rays, hits_dev, want, where):
+    """trq_expand_hits on adversarial rays: the HitRecord fields of every hit, bit for bit (sphere uv: libm vs CUDA)."""
+    from tracer_b200 import rays_to_torch
+    recs = scene.expand(rays_to_torch(rays, f"cuda:{scene.device}"), hits_dev).cpu().numpy().view(L.record_dtype).reshape(-1)
+    w = want["records"]
+    assert np.array_equal(recs["hit"], w["hit"]), where
+    m = w["hit"] == 1
+    sph = want["hits"]["pType"] == L.SPHERE
+    for k in ("t", "p", "gn", "sn", "front", "material"):
+        a, b = recs[k][m].view(np.uint32), w[k][m].view(np.uint32)
+        # a NaN component (0 * inf in a degenerate hit) has no agreed payload: compare NaN-ness there, bits elsewhere
+        if recs[k].dtype.kind == "f":
+            na, nb = np.isnan(recs[k][m]), np.isnan(w[k][m])
+            assert np.array_equal(na, nb) and np.array_equal(a[~na], b[~nb]), f"{where}: {k}"
+        else:
+            assert np.array_equal(a, b), f"{where}: {k}"
+    e = m & ~sph
+    na = np.isnan(w["uv"][e])
+    assert np.array_equal(np.isnan(recs["uv"][e]), na) and np.array_equal(recs["uv"][e].view(np.uint32)[~na], w["uv"][e].view(np.uint32)[~na]), f"{where}: uv"
+
+
 @pytest.mark.parametrize("seed", _seeds())
 def test_adversarial_parity(built, port, seed):
-    _torch()
-    from tracer_b200 import Scene
+    """Every launch configuration of the packed kernel (it finishes the records of all five leaf types itself), both record
+    formats, the reference-layout kernel and the HitRecord expansion, on the adversarial rays."""
+    torch = _torch()
+    from tracer_b200 import Scene, rays_to_torch
     rng = np.random.default_rng(seed)
+    ncfg = len(Scene.kernel_configs())
     for name, prim in scenes(rng):
         scene = Scene(prim, 0)
         rays = adversarial_rays(rng, prim, 40000)
+        d = rays_to_torch(rays, "cuda:0")
         for any_hit in (False, True):
-            want = port.trace(prim, rays, any=any_hit, counters=True, nthreads=8)
-            for reflayout in (False, True):
-                got = gpu_trace(scene, rays, any_hit, reflayout)
-                assert_hits_equal(got, want["hits"], f"{name} seed={seed} any={any_hit} reflayout={reflayout}")
+            want = port.trace(prim, rays, any=any_hit, counters=True, records=not any_hit, nthreads=8)
+            got = gpu_trace(scene, rays, any_hit, True)
+            assert_hits_equal(got, want["hits"], f"{name} seed={seed} any={any_hit} reflayout")
+            for c in range(ncfg):
+                try:
+                    scene.set_kernel_config(c)
+                except Exception:                              # a staged configuration may not fit a deep tree
+                    continue
+                where = f"{name} seed={seed} any={any_hit} cfg={c}"
+                h = scene.hit(d, any=any_hit)
+                got = h.cpu().numpy().view(L.hit_dtype).reshape(-1)
+                assert_hits_equal(got, want["hits"], where)
+                h16 = scene.hit(d, any=any_hit, hit16=True).cpu().numpy().view(L.hit16_dtype).reshape(-1)
+                assert np.array_equal(h16.view(np.uint8), L.pack_hit16(got).view(np.uint8)), where + " hit16"
+                if not any_hit and c == 0:
+                    _assert_records(scene, rays, h, want, where)
+            scene.set_kernel_config(-1)
         scene.close()
