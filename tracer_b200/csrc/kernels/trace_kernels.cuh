@@ -328,7 +328,7 @@ __device__ __noinline__ bool leaf_cube(const RefBVH* __restrict__ bvh, const Ref
 // The final trq_hit of a ray that ended on a sphere / square / cube leaf (the triangle case is inline in flush()).
 //   sphere: Sphere.hh:51-56 (p, gn = (p - c) / r, checkFace, sphereUV)      square: Square.hh:93-111 (uv, checkFace)
 //   cube:   front / material / uv were captured by leaf_cube at hit time
-template <int TAG>
+template <int TAG, bool SQCUBE>
 __device__ __noinline__ void finish_other(const float4* __restrict__ sph, const float4* __restrict__ sq, const RefBVH* __restrict__ bvh,
                                           uint32_t best, float ox, float oy, float oz, float dx, float dy, float dz,
                                           float t, float u, float v, uint32_t aux, float4* out) {
@@ -346,7 +346,7 @@ __device__ __noinline__ void finish_other(const float4* __restrict__ sph, const 
         const float uvy = fdiv(fadd(theta, TRQ_PI_2_F), TRQ_PI_F);
         o0 = make_float4(t, __uint_as_float((uint32_t)TRQ_SPHERE), s1.y, s1.x);
         o1 = make_float4(uvx, uvy, s1.z, __uint_as_float(TRQ_HIT_FLAG_HIT | front));
-    } else if (kind == REF_SQUARE) {
+    } else if (SQCUBE && kind == REF_SQUARE) {
         const float4* qp = sq + (size_t)slot * TRQ_SQ_STRIDE;
         float4 q0, q1;
         ldg8(qp, q0, q1);
@@ -362,7 +362,7 @@ __device__ __noinline__ void finish_other(const float4* __restrict__ sph, const 
         const uint32_t front = front_face(d, gn) ? TRQ_HIT_FLAG_FRONT : 0u;       // :99-100
         o0 = make_float4(t, __uint_as_float((uint32_t)TRQ_SQUARE), q2.x, q1.w);
         o1 = make_float4(uvx, uvy, q1.z, __uint_as_float(TRQ_HIT_FLAG_HIT | front));
-    } else if (kind == REF_CUBE) {
+    } else if (SQCUBE && kind == REF_CUBE) {
         o0 = make_float4(t, __uint_as_float((uint32_t)TRQ_CUBE), __uint_as_float(bvh[slot].pIndex), __uint_as_float(slot));
         o1 = make_float4(u, v, __uint_as_float(aux >> 1), __uint_as_float(TRQ_HIT_FLAG_HIT | ((aux & 1u) ? TRQ_HIT_FLAG_FRONT : 0u)));
     }
@@ -413,7 +413,11 @@ __device__ __forceinline__ void stage_top_of_tree(float4* dst, const float4* src
 
 // ANY: Scene::hit(any = true). OUT: record format. BLOCK x MINB: CTA size and resident CTAs per SM.
 // TOP: the first P.topCount interior nodes are read from shared memory instead of L1/L2.
-template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP>
+// LEAVES: which leaf types the tree has. The code of the absent ones is compiled out: a triangle-only kernel has no
+//       out-of-line call, no stack frame and no register spill (C3 +4 %, C3 primary +6 %); without Square / Cube leaves the
+//       Cube call and its frame go (C1 +5 %, C4 +1 %).
+enum : int { LEAVES_ALL = 0, LEAVES_TRI_SPHERE = 1, LEAVES_TRI = 2 };
+template <bool ANY, int OUT, int BLOCK, int MINB, bool TOP, int LEAVES>
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_packed_kernel(const SceneDev S, const TraceParams P) {
     extern __shared__ __align__(128) uint32_t smem_u32[];
@@ -424,7 +428,8 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     uint32_t* const cold = smem_u32 + topWords + P.stackDepth * BLOCK + threadIdx.x; // [COLD_WORDS][BLOCK]
     float* const coldf = reinterpret_cast<float*>(cold);
     const unsigned lane = threadIdx.x & 31u;
-    constexpr int TAG = (((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0);
+    constexpr int TAG = ((((BLOCK * 8 + MINB) * 2 + (ANY ? 1 : 0)) * 2 + OUT) * 2 + (TOP ? 1 : 0)) * 4 + LEAVES;
+    constexpr bool TRIS = LEAVES == LEAVES_TRI, SQCUBE = LEAVES == LEAVES_ALL;
 
     if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.topSoA, P.topCount, S.topStride, &topBarrier);
 
@@ -460,9 +465,9 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     const uint32_t front = front_face(d, gn) ? TRQ_HIT_FLAG_FRONT : 0u;
                     o0 = make_float4(range_y, __uint_as_float((uint32_t)TRQ_TRIANGLE), q1.w, q0.w);
                     o1 = make_float4(u, v, __uint_as_float(19u), __uint_as_float(TRQ_HIT_FLAG_HIT | front));
-                } else {
+                } else if (!TRIS) {
                     float4 o[2];
-                    finish_other<TAG>(S.sph, S.sq, S.bvh, best, ro.x, ro.y, ro.z, d.x, d.y, d.z, range_y, u, v, cold[COLD_AUX * BLOCK], o);
+                    finish_other<TAG, SQCUBE>(S.sph, S.sq, S.bvh, best, ro.x, ro.y, ro.z, d.x, d.y, d.z, range_y, u, v, cold[COLD_AUX * BLOCK], o);
                     o0 = o[0]; o1 = o[1];
                 }
             }
@@ -588,10 +593,11 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     const float4 t2 = ldg4(tp + 2);
                     h = tri_hit(make_f3(t0.x, t0.y, t0.z), make_f3(t1.x, t1.y, t1.z), make_f3(t2.x, t2.y, t2.z),
                                 ray, FLT_MIN, range_y, t, u, v);
-                } else if (kind == REF_SPHERE) {
+                }
+                else if (!TRIS && kind == REF_SPHERE) {
                     const float4 s0 = ldg4(S.sph + (size_t)TRQ_REF_INDEX(cur) * 2u);
                     h = sphere_hit(make_f3(s0.x, s0.y, s0.z), s0.w, ray, FLT_MIN, range_y, t);
-                } else if (kind == REF_SQUARE) {
+                } else if (SQCUBE && kind == REF_SQUARE) {
                     // Square::hit_test (Square.hh:82-92) on the packed record; the rejections are pure comparisons, and-ed
                     float4 q0, q1;
                     ldg8(S.sq + (size_t)TRQ_REF_INDEX(cur) * TRQ_SQ_STRIDE, q0, q1);
@@ -604,7 +610,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
                     const float sb = fadd(get3(ro, aj), fmul(tt, get3(ray.d, aj)));
                     ok = ok && !(sb < q0.z || sb > q0.w);
                     if (ok) { h = true; t = tt; }
-                } else if (kind == REF_CUBE) {
+                } else if (SQCUBE && kind == REF_CUBE) {
                     float4 o4;
                     h = leaf_cube<TAG>(S.bvh, S.cubes, TRQ_REF_INDEX(cur), ro.x, ro.y, ro.z, ray.d.x, ray.d.y, ray.d.z, range_y, &o4);
                     if (h) { t = o4.x; u = o4.y; v = o4.z; a = __float_as_uint(o4.w); }

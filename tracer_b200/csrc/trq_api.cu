@@ -85,14 +85,13 @@ constexpr size_t kSmemDynamicMax = kSmemPerBlockMax - 1024u;   // dynamic part: 
 struct KernelCfg {
     int block, minb;
     bool top;
-    const void* fn[2][2];
+    const void* fn[3][2][2];      // [leaf types present: LEAVES_*][any][record format]
     const char* name;
 };
-#define TRQ_CFG(B, M, T)                                                                                      \
-    { B, M, T,                                                                                                \
-      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T> }, \
-        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T> } }, \
-      #B "x" #M " top=" #T }
+#define TRQ_CFG_FN(B, M, T, R)                                                                                \
+      { { (const void*)trace_packed_kernel<false, OUT_HIT32, B, M, T, R>, (const void*)trace_packed_kernel<false, OUT_HIT16, B, M, T, R> }, \
+        { (const void*)trace_packed_kernel<true, OUT_HIT32, B, M, T, R>, (const void*)trace_packed_kernel<true, OUT_HIT16, B, M, T, R> } }
+#define TRQ_CFG(B, M, T) { B, M, T, { TRQ_CFG_FN(B, M, T, LEAVES_ALL), TRQ_CFG_FN(B, M, T, LEAVES_TRI_SPHERE), TRQ_CFG_FN(B, M, T, LEAVES_TRI) }, #B "x" #M " top=" #T }
 const KernelCfg kCfgs[] = {
     TRQ_CFG(256, 5, false),       // 0: five CTAs of 256 threads per SM, every node from L1 / L2 (large scenes)
     TRQ_CFG(1024, 1, true),       // 1: one CTA of 1024 threads per SM sharing one TMA-staged copy of the top levels (small trees)
@@ -129,6 +128,7 @@ struct trq_scene {
     uint32_t nNode = 0, nVert = 0, topStride = 0;
     SceneDev dev{};
     uint32_t stackDepth = 1;
+    int leaves = 0;               // LEAVES_*: which leaf types the tree has (selects the kernels without the other types' code)
     uint32_t maxPIndex = 0;       // largest leaf pIndex (trq_hit16 packs it into 28 bits)
     // per launch configuration: staged top-of-tree nodes, dynamic shared memory, resident CTAs per SM [any][format]
     struct CfgState { uint32_t topCount = 0, stackDepth = 0; size_t smem = 0; int blocksPerSM[2][2] = {}; bool usable = false; };
@@ -379,7 +379,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
             P.order = order;
         }
         void* args[2] = {(void*)&s->dev, (void*)&P};
-        TRQ_CUDA(cudaLaunchKernel(K.fn[any ? 1 : 0][hit16 ? 1 : 0], dim3((unsigned)grid), dim3((unsigned)K.block), args, cs.smem, st));
+        TRQ_CUDA(cudaLaunchKernel(K.fn[s->leaves][any ? 1 : 0][hit16 ? 1 : 0], dim3((unsigned)grid), dim3((unsigned)K.block), args, cs.smem, st));
         g_launches++;
         if (scratch) TRQ_CUDA(cudaFreeAsync(scratch, st));
         if (prof) TRQ_CUDA(cudaEventRecord(prof[1], st));
@@ -573,6 +573,8 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
     for (int k = 0; k < 3; ++k) { s->dev.rootMin[k] = rootMin[k]; s->dev.rootMax[k] = rootMax[k]; }
     s->dev.nNode = d->nNode;
     s->stackDepth = info.maxDepth + 1;
+    // (a leaf of unknown pType, which dispatches to `default: break`, also selects the general kernels)
+    s->leaves = info.nLeaf == info.nTri ? LEAVES_TRI : (info.nLeaf == info.nTri + info.nSphere ? LEAVES_TRI_SPHERE : LEAVES_ALL);
     s->scratchPool = trq::scratch_pool(device);                // TRQ_SORT_RAYS scratch: stream-ordered, kept between launches
     if (!s->scratchPool) return trq::fail(TRQ_ERR_CUDA, "cudaMemPoolCreate failed");
     TRQ_LAP(tm, "scratch pool");
@@ -598,8 +600,9 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
         cudaError_t e = cudaSuccess;
         for (int a = 0; a < 2 && e == cudaSuccess; ++a)
             for (int f = 0; f < 2 && e == cudaSuccess; ++f) {
-                if (cs.smem > 48 * 1024) e = cudaFuncSetAttribute(K.fn[a][f], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDynamicMax);
-                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs.blocksPerSM[a][f], K.fn[a][f], K.block, cs.smem);
+                const void* fn = K.fn[s->leaves][a][f];
+                if (cs.smem > 48 * 1024) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemDynamicMax);
+                if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cs.blocksPerSM[a][f], fn, K.block, cs.smem);
                 if (e == cudaSuccess && cs.blocksPerSM[a][f] < 1) cs.usable = false;
             }
         if (e != cudaSuccess) {
@@ -1160,7 +1163,7 @@ int trq_trace_gather(trq_scene* s, trq_gather* g, const trq_ray* rays, uint64_t 
     // driver sizes the SM's shared-memory carve-out to what the trace needs, rounded up to a supported size; when that leaves
     // less than the reserve (C3's depth: 5 x 39 KB = 195 of 196 KB), ask for the next size for this launch.
     const bool any = (flags & TRQ_TRACE_ANY) != 0, hit16 = (flags & TRQ_HIT16) != 0;
-    const void* fn = kCfgs[0].fn[any ? 1 : 0][hit16 ? 1 : 0];
+    const void* fn = kCfgs[0].fn[s->leaves][any ? 1 : 0][hit16 ? 1 : 0];
     bool bumped = false, useTma = false;
     if (n) {
         static const size_t kCarveKB[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
