@@ -333,7 +333,7 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
     } else {
         static const uint32_t refillMin = [] {
             const char* e = getenv("TRQ_REFILL_MIN");
-            int v = e ? atoi(e) : 16;      // B200 sweeps (profiles/r01_sweep*): 12..20 is flat within 2% on C3
+            int v = e ? atoi(e) : 20;      // B200 sweeps: 16..22 within 2 % (profiles/r02_refill_sweep.txt: 20 is +1 % on C3, +2 % on C4 over 16)
             return (uint32_t)(v < 1 ? 1 : (v > 32 ? 32 : v));
         }();
         static const uint32_t leafBatch = [] {
