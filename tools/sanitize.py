@@ -57,6 +57,18 @@ idx = torch.from_numpy(prim.idxList.view(np.uint8).reshape(-1).copy()).cuda()
 ds = Scene(DevicePrimitive(triList=tri, idxList=idx, bvhList=nodes), 0)
 ds.hit(r0)
 ds.update_vertices(tri); ds.hit(r0, any=True)
+# the kernels specialised by leaf types: triangles only (ds) and triangles + spheres (C1's spheres), every configuration
+sp = Scene(H.scene_c1(), 0)
+rs = scene.cast_rays((13, 2, 3), (0, 0, 0), (0, 1, 0), np.float32(20 * np.pi / 180), 96, 54)
+for sc, rr in ((ds, r0), (sp, rs)):
+    for c in range(len(Scene.kernel_configs())):
+        try:
+            sc.set_kernel_config(c)
+        except Exception:
+            continue
+        for h16 in (False, True):
+            sc.hit(rr, hit16=h16); sc.hit(rr, any=True, hit16=h16)
+    sc.set_kernel_config(-1)
 dm = Scene(DevicePrimitive.from_host(prim, "cuda:0"), 0)     # mixed leaves through the device planner
 assert torch.equal(dm.hit(r0).view(torch.int32), h0.view(torch.int32))
 torch.cuda.synchronize()
