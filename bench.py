@@ -737,7 +737,7 @@ def run_gpu_arm(a):
     main_roof = roofline_of(a.workload, bpr, n, m["kernel_ms"], m["ms_per_step"], work.launches_per_step, hbm_peak, peak_src, l2_gbs,
                             traffic.get(a.workload + ("_sorted" if sort and a.workload + "_sorted" in traffic else "")))
     main_cfg = config_of(a.workload, work.prim, n, sort, a.flush_l2, world)
-    kernel_cfg = scene.kernel_configs()[0]
+    kernel_cfg = scene.kernel_config()
     work.close()
     del d_hits_ref
     torch.cuda.empty_cache()
@@ -757,7 +757,7 @@ def run_gpu_arm(a):
                 e = {"config": WORKLOADS[wname], "query": "any-hit" if w.any_hit else "closest-hit", "value": round(r["value"], 2), "unit": UNIT,
                      "steps": steps, "ms_per_step": round(r["ms_per_step"], 4), "rays_per_step_per_gpu": int(w.n),
                      "scaling": "strong" if wname == "c5" else "weak", "gpu_launches": r["launches"],
-                     "ray_ordering": "TRQ_SORT_RAYS" if w.sort else "as given"}
+                     "ray_ordering": "TRQ_SORT_RAYS" if w.sort else "as given", "kernel_config": w.scene.kernel_config()}
                 if rank == 0:
                     try:
                         wb = bytes_per_ray(w, nthreads)

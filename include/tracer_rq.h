@@ -180,6 +180,8 @@ int  trq_scene_info(const trq_scene* scene, trq_scene_info_t* info);
 int  trq_kernel_config_count(void);
 const char* trq_kernel_config_name(int cfg);
 int  trq_scene_set_kernel_config(trq_scene* scene, int cfg, uint32_t* topNodesStaged);
+/* The configuration this scene's traces use now (index into trq_kernel_config_name), or -1 for a NULL scene. */
+int  trq_scene_kernel_config(const trq_scene* scene);
 
 /* Scene::hit for n rays. Device pointers unless TRQ_HOST_PTRS; asynchronous on `stream`
  * (a cudaStream_t, NULL = default stream) for device pointers. Re-entrant across streams and host threads (any number

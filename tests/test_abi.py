@@ -144,6 +144,7 @@ def test_round2_entry_points_fail_loudly_without_a_device_or_arguments(built):
     assert lib.trq_scene_update_vertices(None, None, 0, 0) == ERR_INVALID
     assert lib.trq_bvh_build_tree_device(None, 0, 0, None, None) == ERR_INVALID
     assert lib.trq_scene_set_kernel_config(None, 0, None) == ERR_INVALID
+    assert lib.trq_scene_kernel_config(None) == -1
     assert lib.trq_kernel_config_count() >= 2 and lib.trq_kernel_config_name(0).startswith(b"256x5")
     assert lib.trq_kernel_config_name(99) is None
     if not torch.cuda.is_available():

@@ -50,7 +50,7 @@ class Camera(C.Structure):
 ABI_SYMBOLS = [
     "trq_version", "trq_last_error_string", "trq_device_count",
     "trq_scene_create", "trq_scene_create_device", "trq_scene_update_vertices", "trq_scene_destroy", "trq_device_trim", "trq_scene_info",
-    "trq_kernel_config_count", "trq_kernel_config_name", "trq_scene_set_kernel_config",
+    "trq_kernel_config_count", "trq_kernel_config_name", "trq_scene_set_kernel_config", "trq_scene_kernel_config",
     "trq_trace", "trq_host_sync", "trq_expand_hits", "trq_launch_count", "trq_profile_enable", "trq_profile_read", "trq_probe_bandwidth",
     "trq_bvh_build_node", "trq_bvh_build_nodes_triangles", "trq_bvh_build_tree", "trq_bvh_build_tree_gpu", "trq_bvh_build_tree_device",
     "trq_cast_rays", "trq_trace_indirect", "trq_spawn_bounce", "trq_spawn_shadow", "trq_spawn_bounce_rng", "trq_spawn_shadow_rng", "trq_rng_frame_begin",
@@ -78,6 +78,7 @@ lib.trq_scene_info.argtypes = [_vp, C.POINTER(SceneInfo)]
 lib.trq_kernel_config_name.argtypes = [C.c_int]
 lib.trq_kernel_config_name.restype = C.c_char_p
 lib.trq_scene_set_kernel_config.argtypes = [_vp, C.c_int, C.POINTER(_u32)]
+lib.trq_scene_kernel_config.argtypes = [_vp]
 lib.trq_trace.argtypes = [_vp, _vp, _u64, _u32, _vp, _vp]
 lib.trq_host_sync.argtypes = [_vp]
 lib.trq_expand_hits.argtypes = [_vp, _vp, _vp, _u64, _u32, _vp, _vp]

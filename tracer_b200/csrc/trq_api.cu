@@ -812,6 +812,8 @@ int trq_scene_set_kernel_config(trq_scene* s, int cfg, uint32_t* topNodesStaged)
     return TRQ_OK;
 }
 
+int trq_scene_kernel_config(const trq_scene* s) { return s ? pick_cfg(s) : -1; }
+
 int trq_scene_info(const trq_scene* s, trq_scene_info_t* info) {
     if (!s || !info) return trq::fail(TRQ_ERR_INVALID, "trq_scene_info: NULL argument");
     *info = s->info;

@@ -226,6 +226,10 @@ class Scene:
         check(lib.trq_scene_set_kernel_config(self._h, int(cfg), C.byref(staged)), "trq_scene_set_kernel_config")
         return staged.value
 
+    def kernel_config(self):
+        """Name of the launch configuration this scene's traces use now."""
+        return self.kernel_configs()[lib.trq_scene_kernel_config(self._h)]
+
     def host_sync(self):
         check(lib.trq_host_sync(self._h), "trq_host_sync")
 
