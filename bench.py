@@ -578,8 +578,9 @@ def measure_gather(D, work, steps, rank, world):
     out["value"] = out["trq_hit"]["value"]
     out["ms_per_step"] = out["trq_hit"]["ms_per_step"]
     out["all_slots_match"] = out["trq_hit"]["all_slots_match"] and out["trq_hit16"]["all_slots_match"]
-    out["how"] = ("trq_trace_gather: the trace kernel counts finished records per 4096-record tile; a sender kernel sharing the SMs with it ships "
-                  "each complete tile to every rank's buffer over NVLink peer memory (coalesced stores, under the traversal) and publishes (count, step)")
+    out["how"] = ("trq_trace_gather: the trace kernel counts finished records per 2048-record tile; a TMA sender kernel sharing the SMs "
+                  "with it (one thread per SM, cp.async.bulk through 2 x 12 KB of shared memory) ships each complete tile to every rank's "
+                  "buffer over NVLink peer memory, under the traversal, and publishes (count, step)")
     return out
 
 
