@@ -13,9 +13,13 @@
 //                           ties to the right child, the far child decided at first arrival and never
 //                           re-tested, including the "select the missed child" quirk of Render.hh:174.
 //                           A retiring ray's FINAL record (trq_hit, or the 16-byte trq_hit16) is written by
-//                           this kernel for every leaf type -- there is no second pass over the batch -- and,
-//                           when a gather is attached, stored into every peer GPU's buffer from the same
-//                           place (compute + all-gather in one kernel, over NVLink peer memory).
+//                           this kernel for every leaf type -- there is no second pass over the batch. One
+//                           instance per set of leaf types a tree can have (LEAVES), so that a mesh scene
+//                           carries no Sphere / Square / Cube code. Under trq_trace_gather it also counts the
+//                           finished records of every tile, for:
+//   gather_send_tma_kernel  the collective half of trq_trace_gather: resident BESIDE the trace kernel, ships each
+//                           complete tile of records to every peer GPU with TMA bulk copies over NVLink peer
+//                           memory while the traversal is still running (gather_send_kernel: the LSU fallback)
 //   sort_*_kernel           optional ordering of the work queue (TRQ_SORT_RAYS)
 //   expand_hits_kernel      trq_hit -> HitRecord fields (p, gn, sn, uv, f, material)
 //   pack_scene_kernel       reference-layout arrays -> packed traversal layout, on the device
