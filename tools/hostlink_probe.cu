@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <chrono>
+#include <vector>
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
@@ -143,6 +144,35 @@ int main(int argc, char** argv) {
             if (rep > 0 && ms < best) best = ms;
         }
         printf("pipeline %2zu MB chunks, %d streams, kernel x%d   %7.3f ms wall  %6.1f GB/s per direction\n", chunkMB, S, reps, best, bytes / best / 1e6);
+    }
+    // the same pipeline with chunk sizes ramping up at the start and down at the end (first trace starts sooner, last D2H is shorter)
+    for (int reps : {0, 8}) for (int S : {4, 8}) for (size_t firstMB : {1, 2, 4}) {
+        std::vector<size_t> sizes;
+        { size_t left = bytes; size_t c = firstMB << 20; const size_t full = 16u << 20;
+          std::vector<size_t> up; for (; c < full; c *= 2) up.push_back(c);
+          size_t upSum = 0; for (size_t v : up) upSum += v;
+          for (size_t v : up) sizes.push_back(v);
+          left -= 2 * upSum;
+          while (left > full) { sizes.push_back(full); left -= full; }
+          if (left) sizes.push_back(left);
+          for (size_t k = up.size(); k-- > 0;) sizes.push_back(up[k]); }
+        float best = 1e9f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaDeviceSynchronize());
+            const auto t0 = std::chrono::steady_clock::now();
+            size_t off = 0; int k = 0;
+            for (size_t len : sizes) {
+                cudaStream_t st = ps[k++ % S];
+                CK(cudaMemcpyAsync(dA + off, hIn + off, len, cudaMemcpyHostToDevice, st));
+                if (reps) chunk_kernel<<<sms * 4, 256, 0, st>>>((const uint4*)(dA + off), (uint4*)(dB + off), len / 16, reps);
+                CK(cudaMemcpyAsync(hOut + off, dB + off, len, cudaMemcpyDeviceToHost, st));
+                off += len;
+            }
+            CK(cudaDeviceSynchronize());
+            const float ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (rep > 0 && ms < best) best = ms;
+        }
+        printf("pipeline ramp %zu..16..%zu MB (%zu chunks), %d streams, kernel x%d   %7.3f ms wall  %6.1f GB/s per direction\n", firstMB, firstMB, sizes.size(), S, reps, best, bytes / best / 1e6);
     }
     return 0;
 }
