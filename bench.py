@@ -196,6 +196,8 @@ class Work:
             def step():
                 scene.hit(d_rays, any=any_hit, out=d_hits, sort=sort)
             self.step = step
+            # the same batch WITHOUT the TRQ_SORT_RAYS hint: on a tree much larger than L2 the library examines the batch itself
+            self.step_unhinted = lambda: scene.hit(d_rays, any=any_hit, out=d_hits, sort=None)
 
     def hits(self):
         """Device hit records of the last step (wavefronts: primary wave, then the bounce wave)."""
@@ -359,6 +361,19 @@ def measure(D, work, steps, warmup, flush=None, sampler=None):
     return {"total_ms": total_ms, "total_rays": total_rays, "value": total_rays * steps / total_ms / 1e3,
             "ms_per_step": total_ms / steps, "launches": int(launches),
             "kernel_ms": trace_ms / max(1, nl) * work.launches_per_step}
+
+
+def measure_unhinted(D, work, steps):
+    """C5 without the caller's hint: the library's own coherence check decides (three extra launches per step inside the timed region)."""
+    import torch
+    for _ in range(3):
+        work.step_unhinted()
+    torch.cuda.synchronize()
+    ms, _, _ = time_steps(D, work.step_unhinted, steps)
+    total_ms = D.max_over_ranks(ms)
+    return {"value": round(D.sum_over_ranks(work.n) * steps / total_ms / 1e3, 2), "unit": UNIT, "steps": steps,
+            "ms_per_step": round(total_ms / steps, 4),
+            "how": "no TRQ_SORT_RAYS flag: a probe over 64 K sampled rays measures how many neighbouring rays share (cell, octant); the queue is ordered when fewer than half do"}
 
 
 def bytes_per_ray(work, nthreads):
@@ -619,6 +634,7 @@ def run_gpu_arm(a):
         sampler.mark("timed region + the same step sustained for >= 0.6 s", t0, t1)
         s_ms = D.max_over_ranks(ms)
         sustained = {"value": round(total_rays * k / s_ms / 1e3, 2), "unit": UNIT, "steps": k, "seconds": round(s_ms / 1e3, 3)}
+    unhinted = measure_unhinted(D, work, min(a.steps, 5)) if a.workload == "c5" and sort else None
     hit_frac = float((work.hits()[:, 7].view(torch.int32) & 1).float().mean())
     d_hits_ref = work.hits().clone()
 
@@ -769,6 +785,8 @@ def run_gpu_arm(a):
                         log(f"# {wname}: oracle unavailable: {ex!r}")
                     e["roofline"] = roofline_of(wname, wb, w.n, r["kernel_ms"], r["ms_per_step"], w.launches_per_step, hbm_peak, peak_src, l2_gbs,
                                                 traffic.get(wname + "_sorted" if w.sort and wname + "_sorted" in traffic else wname))
+                if wname == "c5":
+                    e["unhinted"] = measure_unhinted(D, w, min(steps, 5))
                 extras[wname] = e
                 w.close()
                 del w
@@ -797,6 +815,8 @@ def run_gpu_arm(a):
     }
     if sustained is not None:
         line["sustained"] = sustained
+    if unhinted is not None:
+        line["unhinted"] = unhinted
     line.update(e2e_extra)
     if gathered is not None:
         line["gathered_hits_checked"] = gathered

@@ -133,8 +133,12 @@ typedef struct trq_scene_info_t {
                                        (chunked, overlapped with tracing) and returns after completion */
 #define TRQ_KERNEL_REFLAYOUT 0x4u   /* run the 1:1 transcription over the reference-layout buffers
                                        (correctness anchor / naive baseline) instead of the packed kernel */
-#define TRQ_SORT_RAYS        0x8u   /* hint: the batch is incoherent; the library may order the work queue by
-                                       (origin cell, direction octant) first. Results are identical either way. */
+#define TRQ_SORT_RAYS        0x8u   /* hint: the batch is incoherent; the library orders the work queue by
+                                       (origin cell, direction octant) first. Results are identical either way.
+                                       Without the hint, a scene whose packed tree exceeds twice the L2 cache has its
+                                       batches of >= 2^20 rays examined (one streaming pass) and ordered when fewer than
+                                       half of the neighbouring rays share a cell and octant. */
+#define TRQ_NO_SORT          0x40u  /* never order the work queue (switches the automatic mode off for this call) */
 
 #define TRQ_HIT16            0x20u  /* `hits` is trq_hit16[n] (16-byte aligned) instead of trq_hit[n] */
 

@@ -100,3 +100,34 @@ def test_host_path_chunk_boundaries(built):
     finally:
         del os.environ["TRQ_CHUNK_RAYS"]
     scene.close()
+
+
+def test_automatic_ray_ordering(built, port):
+    """Without TRQ_SORT_RAYS, a scene whose tree is much larger than L2 has large batches examined on the device: incoherent
+    ones are ordered before the traversal, coherent ones are left as given. TRQ_AUTO_SORT=1 applies the rule to a small
+    scene here. Whatever it decides, every ray's record lands at the ray's own index and equals the unordered result."""
+    import os
+    torch = _torch()
+    from tracer_b200 import Scene, harness as H, rays_to_torch
+    prim = H.scene_soup(100000, seed=21, extent=0.02)
+    scene = Scene(prim, 0)
+    n = (1 << 20) + 12345
+    incoherent = H.random_rays(n, seed=4)
+    coherent = np.repeat(H.camera_rays((0.5, 0.5, -2.0), (0.5, 0.5, 0.5), np.float32(0.6), 1280, 720), 2)[:n]   # neighbours share cell and octant
+    os.environ["TRQ_AUTO_SORT"] = "1"
+    try:
+        for rays in (incoherent, coherent):
+            d = rays_to_torch(np.ascontiguousarray(rays), "cuda:0")
+            plain = scene.hit(d, sort=False).clone()                 # TRQ_NO_SORT
+            for any_hit in (False, True):
+                ref = scene.hit(d, any=any_hit, sort=False).clone()
+                auto = scene.hit(d, any=any_hit)                       # the library decides
+                hinted = scene.hit(d, any=any_hit, sort=True)
+                assert torch.equal(auto.view(torch.int32), ref.view(torch.int32))
+                assert torch.equal(hinted.view(torch.int32), ref.view(torch.int32))
+            sub = np.arange(0, rays.size, 97)
+            want = port.trace(prim, np.ascontiguousarray(rays[sub]), nthreads=8)["hits"]
+            assert_hits_equal(plain.cpu().numpy().view(L.hit_dtype).reshape(-1)[sub], want, "auto ordering")
+    finally:
+        del os.environ["TRQ_AUTO_SORT"]
+    scene.close()

@@ -40,6 +40,10 @@ def workloads(name):
         sets = {"random": (rays, False, False)}
         if n >= 10_000_000:
             sets["random_sorted"] = (rays, False, True)
+            sets["random_auto"] = (rays, False, None)                # no hint: the library examines the batch (large tree)
+            cam = H.camera_rays((0.5, 0.5, -1.5), (0.5, 0.5, 0.5), np.float32(0.7), 3840, 2160)
+            sets["camera"] = (cam, False, False)
+            sets["camera_auto"] = (cam, False, None)
         return prim, scene, sets
     raise SystemExit(f"unknown workload {name}")
 

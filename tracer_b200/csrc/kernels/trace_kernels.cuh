@@ -196,25 +196,56 @@ __device__ __forceinline__ uint32_t ray_sort_key(const SceneDev& S, const float4
 // Both atomic passes are warp-aggregated (__match_any_sync): lanes with the same key elect one leader that
 // issues a single atomicAdd for the group, so a batch whose rays all share one bin (e.g. primary rays from one
 // eye point) costs n/32 same-address atomics, not n.
+// Automatic mode (no TRQ_SORT_RAYS hint, tree much larger than L2): a probe over 2048 evenly spread runs of 32 consecutive rays
+// counts how many neighbouring rays share a key: ctrl[0] = pairs with equal keys, ctrl[2] = pairs looked at. The batch counts as
+// INCOHERENT -- worth ordering -- when fewer than half of them do (uniform random rays: ~0; bounce rays off neighbouring pixels:
+// ~1/8; primary and shadow rays: nearly all). Every consumer (the three sort passes, the trace kernel) evaluates the same predicate
+// from the same two counters, so the decision costs no extra pass and no host round trip; a coherent batch pays the probe and
+// three launches that return at once.
+__device__ __forceinline__ bool batch_is_incoherent(const uint32_t* ctrl) { return 2u * __ldg(ctrl) < __ldg(ctrl + 2); }
+
 __global__ void __launch_bounds__(256)
-sort_count_kernel(SceneDev S, const trq_ray* __restrict__ rays, uint64_t n, const unsigned long long* __restrict__ nPtr,
-                  uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < live_count(n, nPtr);
-    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-    if (!valid) return;
+sort_probe_kernel(SceneDev S, const trq_ray* __restrict__ rays, uint64_t n, const unsigned long long* __restrict__ nPtr,
+                  uint32_t* __restrict__ ctrl) {
+    const uint64_t runs = live_count(n, nPtr) / 32u;
+    if (runs == 0) return;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5, w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t i = (w * runs / warps) * 32u + lane;
     const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
     const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
     const uint32_t key = ray_sort_key(S, r0, r1);
-    keys[i] = key;
-    const unsigned peers = __match_any_sync(vm, key);
-    if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+    const uint32_t next = __shfl_down_sync(0xffffffffu, key, 1);
+    const unsigned same = __ballot_sync(0xffffffffu, lane < 31u && next == key);
+    if (lane == 0) { atomicAdd(&ctrl[0], (uint32_t)__popc(same)); atomicAdd(&ctrl[2], 31u); }
+}
+
+// (count and scatter walk the batch with a grid-stride loop over a capped grid, so that the launches that return at once in
+// the automatic mode cost microseconds, not the scheduling of n / 256 empty CTAs)
+__global__ void __launch_bounds__(256)
+sort_count_kernel(SceneDev S, const trq_ray* __restrict__ rays, uint64_t n, const unsigned long long* __restrict__ nPtr,
+                  uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, const uint32_t* __restrict__ ctrl) {
+    if (ctrl && !batch_is_incoherent(ctrl)) return;             // automatic mode found the batch coherent: the queue stays as given
+    const uint64_t N = live_count(n, nPtr);
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < N; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const bool valid = i < N;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        const float4 r0 = ldg4(reinterpret_cast<const float4*>(rays + i));
+        const float4 r1 = ldg4(reinterpret_cast<const float4*>(rays + i) + 1);
+        const uint32_t key = ray_sort_key(S, r0, r1);
+        keys[i] = key;
+        const unsigned peers = __match_any_sync(vm, key);
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[key], (uint32_t)__popc(peers));
+    }
 }
 
 // exclusive prefix sum of TRQ_SORT_BINS counters, one CTA of 1024 threads (256 bins per thread)
 __global__ void __launch_bounds__(1024)
-sort_scan_kernel(uint32_t* __restrict__ hist) {
+sort_scan_kernel(uint32_t* __restrict__ hist, const uint32_t* __restrict__ ctrl) {
     __shared__ uint32_t partial[1024];
+    if (ctrl && !batch_is_incoherent(ctrl)) return;
     const uint32_t per = TRQ_SORT_BINS / 1024u;
     uint32_t* mine = hist + threadIdx.x * per;
     uint32_t sum = 0;
@@ -233,19 +264,23 @@ sort_scan_kernel(uint32_t* __restrict__ hist) {
 
 __global__ void __launch_bounds__(256)
 sort_scatter_kernel(const uint32_t* __restrict__ keys, uint64_t n, const unsigned long long* __restrict__ nPtr,
-                    uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < live_count(n, nPtr);
-    const unsigned vm = __ballot_sync(0xffffffffu, valid);
-    if (!valid) return;
-    const uint32_t key = keys[i];
+                    uint32_t* __restrict__ cursor, uint32_t* __restrict__ order, const uint32_t* __restrict__ ctrl) {
+    if (ctrl && !batch_is_incoherent(ctrl)) return;
+    const uint64_t N = live_count(n, nPtr);
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned peers = __match_any_sync(vm, key);
-    const unsigned leader = (unsigned)(__ffs(peers) - 1);
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    order[base + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;     // lanes keep their index order inside a group
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < N; base += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = base + threadIdx.x;
+        const bool valid = i < N;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        const uint32_t key = keys[i];
+        const unsigned peers = __match_any_sync(vm, key);
+        const unsigned leader = (unsigned)(__ffs(peers) - 1);
+        uint32_t slot = 0;
+        if (lane == leader) slot = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+        slot = __shfl_sync(peers, slot, leader);
+        order[slot + (uint32_t)__popc(peers & ((1u << lane) - 1u))] = (uint32_t)i;     // lanes keep their index order inside a group
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,6 +302,7 @@ struct TraceParams {
     uint32_t       topCount;       // interior nodes [0, topCount) are staged in shared memory (TOP kernels), else 0
     uint32_t       pad0, pad1;
     const uint32_t* order;         // optional queue order (TRQ_SORT_RAYS): queue slot -> ray index; NULL = identity
+    const uint32_t* orderFlag;     // optional (automatic mode): the probe's counters; `order` applies only if batch_is_incoherent()
     const unsigned long long* nPtr;    // optional device-resident batch size (trq_trace_indirect); n is then the capacity
     // trq_trace_gather: every finished record also counts towards its tile of TRQ_GATHER_TILE consecutive records
     // (tileDone[index >> shift], after a fence), so that gather_send_kernel -- running beside this kernel -- can ship each
@@ -438,6 +474,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
     if (TOP) stage_top_of_tree(reinterpret_cast<float4*>(smem_u32), S.topSoA, P.topCount, S.topStride, &topBarrier);
 
     const uint64_t N = live_count(P.n, P.nPtr);
+    const bool useOrder = P.order != nullptr && (P.orderFlag == nullptr || batch_is_incoherent(P.orderFlag));
     bool active = false, exhausted = false;
     f3 ro = make_f3(0.f, 0.f, 0.f), rinv = make_f3(0.f, 0.f, 0.f);
     float range_y = 0.0f;
@@ -495,7 +532,7 @@ trace_packed_kernel(const SceneDev S, const TraceParams P) {
         if (base + (unsigned long long)want >= N) exhausted = true;
         const uint64_t slot = base + (uint64_t)__popc(mask & ((1u << lane) - 1u));
         if (!((mask >> lane) & 1u) || slot >= N) return ~0ull;
-        return P.order ? (uint64_t)__ldg(P.order + slot) : slot;
+        return useOrder ? (uint64_t)__ldg(P.order + slot) : slot;
     };
 
     for (;;) {

@@ -128,6 +128,7 @@ struct trq_scene {
     uint32_t nNode = 0, nVert = 0, topStride = 0;
     SceneDev dev{};
     uint32_t stackDepth = 1;
+    bool largeTree = false;       // packed tree > 2 x L2: incoherent batches are worth ordering (automatic TRQ_SORT_RAYS)
     int leaves = 0;               // LEAVES_*: which leaf types the tree has (selects the kernels without the other types' code)
     uint32_t maxPIndex = 0;       // largest leaf pIndex (trq_hit16 packs it into 28 bits)
     // per launch configuration: staged top-of-tree nodes, dynamic shared memory, resident CTAs per SM [any][format]
@@ -360,23 +361,34 @@ int launch_trace(trq_scene* s, const trq_ray* d_rays, uint64_t n, uint32_t flags
         P.topCount = K.top ? cs.topCount : 0;
         P.order = nullptr; P.nPtr = nPtr;
         P.tileDone = tileDone; P.tileShift = tileShift;
-        // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch
-        // strictly opt-in (the caller knows whether its batch is incoherent, e.g. bounce depth >= 1 in a scene
-        // that does not fit L2); TRQ_SORT_RAYS=0/1 in the environment overrides for experiments.
+        // TRQ_SORT_RAYS: counting sort of ray indices by (origin cell, direction octant); stream-ordered scratch. The flag is the
+        // caller's word that the batch is incoherent. Without it, scenes whose packed tree is more than twice the L2 (where an
+        // incoherent batch runs at DRAM latency: C5 400 vs 990 Mrays/s) get the AUTOMATIC mode for batches of >= 1 M rays: a
+        // probe over 64 K sampled rays measures how many neighbouring rays share a key, and the queue is ordered only if fewer
+        // than half do -- decided on the device, no host round trip. TRQ_NO_SORT opts out; TRQ_SORT_RAYS=0/1 in the environment overrides
+        // both (experiments), TRQ_AUTO_SORT=1 treats every scene as large (tests).
         static const int sortEnv = [] { const char* e = getenv("TRQ_SORT_RAYS"); return e ? atoi(e) : -1; }();
+        const char* autoStr = getenv("TRQ_AUTO_SORT");           // read per call: the tests switch it inside one process
+        const int autoEnv = autoStr ? atoi(autoStr) : -1;
         const bool sortRays = sortEnv >= 0 ? (sortEnv != 0) : ((flags & TRQ_SORT_RAYS) != 0);
+        const bool autoSort = !sortRays && sortEnv < 0 && !(flags & TRQ_NO_SORT) && !tileDone && n >= (1ull << 20) &&
+                              (autoEnv >= 0 ? autoEnv != 0 : s->largeTree);
         uint32_t* scratch = nullptr;
-        if (sortRays && n >= 65536) {
-            const size_t words = (size_t)TRQ_SORT_BINS + 2 * (size_t)n;          // hist | keys | order
+        if ((sortRays && n >= 65536) || autoSort) {
+            const size_t words = (size_t)TRQ_SORT_BINS + 4 + 2 * (size_t)n;      // hist | ctrl | keys | order
             TRQ_CUDA(cudaMallocFromPoolAsync((void**)&scratch, words * sizeof(uint32_t), s->scratchPool, st));
-            uint32_t* hist = scratch; uint32_t* keys = scratch + TRQ_SORT_BINS; uint32_t* order = keys + n;
-            TRQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)TRQ_SORT_BINS * sizeof(uint32_t), st));
-            const unsigned gb = (unsigned)((n + 255) / 256);
-            sort_count_kernel<<<gb, 256, 0, st>>>(s->dev, d_rays, n, nPtr, keys, hist);
-            sort_scan_kernel<<<1, 1024, 0, st>>>(hist);
-            sort_scatter_kernel<<<gb, 256, 0, st>>>(keys, n, nPtr, hist, order);
+            uint32_t* hist = scratch; uint32_t* ctrl = scratch + TRQ_SORT_BINS; uint32_t* keys = ctrl + 4; uint32_t* order = keys + n;
+            TRQ_CUDA(cudaMemsetAsync(hist, 0, ((size_t)TRQ_SORT_BINS + 4) * sizeof(uint32_t), st));
+            unsigned gb = (unsigned)((n + 255) / 256);
+            if (gb > (unsigned)s->numSMs * 32u) gb = (unsigned)s->numSMs * 32u;   // grid-stride beyond that
+            uint32_t* decide = autoSort ? ctrl : nullptr;
+            if (autoSort) { sort_probe_kernel<<<256, 256, 0, st>>>(s->dev, d_rays, n, nPtr, ctrl); g_launches++; }
+            sort_count_kernel<<<gb, 256, 0, st>>>(s->dev, d_rays, n, nPtr, keys, hist, decide);
+            sort_scan_kernel<<<1, 1024, 0, st>>>(hist, decide);
+            sort_scatter_kernel<<<gb, 256, 0, st>>>(keys, n, nPtr, hist, order, decide);
             g_launches += 3;
             P.order = order;
+            P.orderFlag = decide;
         }
         void* args[2] = {(void*)&s->dev, (void*)&P};
         TRQ_CUDA(cudaLaunchKernel(K.fn[s->leaves][any ? 1 : 0][hit16 ? 1 : 0], dim3((unsigned)grid), dim3((unsigned)K.block), args, cs.smem, st));
@@ -624,6 +636,11 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
                                 (uint64_t)d->nCube * sizeof(RefCube) + (uint64_t)d->nVert * sizeof(RefVertex) +
                                 (uint64_t)d->nTri * 12 + (uint64_t)d->nNode * sizeof(RefBVH);
     info.bytesPacked = nodeBytes + triBytes + sphBytes + sqBytes + triNBytes;
+    {
+        int l2 = 0;
+        if (cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, device) != cudaSuccess) { cudaGetLastError(); l2 = 0; }
+        s->largeTree = l2 > 0 && (uint64_t)(nodeBytes + triBytes + sphBytes + sqBytes) > 2ull * (uint64_t)l2;   // what traversal touches
+    }
     info.device = device;
     s->info = info;
     return TRQ_OK;

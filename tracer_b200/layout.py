@@ -68,7 +68,7 @@ assert sphere_dtype.itemsize == 272 and square_dtype.itemsize == 272 and cube_dt
 assert ray_dtype.itemsize == 32 and hit_dtype.itemsize == 32 and hit16_dtype.itemsize == 16 and record_dtype.itemsize == 64
 
 HIT_FLAG_HIT, HIT_FLAG_FRONT = 1, 2
-TRACE_ANY, HOST_PTRS, KERNEL_REFLAYOUT, SORT_RAYS, HOST_ASYNC, HIT16 = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
+TRACE_ANY, HOST_PTRS, KERNEL_REFLAYOUT, SORT_RAYS, HOST_ASYNC, HIT16, NO_SORT = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
 
 FLT_MAX = float(np.finfo(np.float32).max)
 FLT_MIN = float(np.finfo(np.float32).tiny)

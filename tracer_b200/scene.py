@@ -181,11 +181,12 @@ class Scene:
     __del__ = close
 
     # ---- Scene::hit over a batch ------------------------------------------------------------
-    def hit(self, rays, any=False, out=None, reflayout=False, stream=None, sort=False, hit16=False):
+    def hit(self, rays, any=False, out=None, reflayout=False, stream=None, sort=None, hit16=False):
         """rays: torch CUDA float32 tensor (n, 8) -> returns torch CUDA float32 tensor (n, 8) holding
         trq_hit rows (view as int32 for the id fields); or numpy `ray_dtype` array -> numpy `hit_dtype`.
-        hit16=True: the 16-byte trq_hit16 records instead ((n, 4) float32 tensor / `hit16_dtype` array)."""
-        flags = (L.TRACE_ANY if any else 0) | (L.KERNEL_REFLAYOUT if reflayout else 0) | (L.SORT_RAYS if sort else 0) | (L.HIT16 if hit16 else 0)
+        hit16=True: the 16-byte trq_hit16 records instead ((n, 4) float32 tensor / `hit16_dtype` array).
+        sort: True = TRQ_SORT_RAYS (the batch is incoherent), False = TRQ_NO_SORT, None = the library decides (large trees only)."""
+        flags = (L.TRACE_ANY if any else 0) | (L.KERNEL_REFLAYOUT if reflayout else 0) | _sort_flag(sort) | (L.HIT16 if hit16 else 0)
         width = 4 if hit16 else 8
         if isinstance(rays, np.ndarray):
             if rays.dtype != L.ray_dtype:
@@ -315,6 +316,10 @@ class Scene:
         check(lib.trq_expand_hits(self._h, rays.data_ptr(), hits.data_ptr(), n, 0, recs.data_ptr(), C.c_void_p(st)),
               "trq_expand_hits")
         return recs
+
+
+def _sort_flag(sort):
+    return 0 if sort is None else (L.SORT_RAYS if sort else L.NO_SORT)
 
 
 class MultiGpuScene:
