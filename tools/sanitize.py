@@ -30,6 +30,12 @@ scene.set_kernel_config(-1)
 h0 = scene.hit(r0, sort=True) if r0.shape[0] >= 65536 else scene.hit(r0)
 big = torch.cat([r0] * 16)
 scene.hit(big, sort=True)
+# automatic ordering (probe + the passes that may return at once): needs >= 2^20 rays; an incoherent and a coherent batch
+os.environ["TRQ_AUTO_SORT"] = "1"
+huge = torch.cat([r0] * 203)
+scene.hit(huge)                                                    # camera rays repeated: coherent
+scene.hit(huge[torch.randperm(huge.shape[0], device=huge.device)].contiguous())   # shuffled: incoherent
+del os.environ["TRQ_AUTO_SORT"]
 scene.expand(r0, h0)
 r1, s1, c1 = scene.spawn_bounce(r0, h0, seed_base=3)
 h1 = scene.hit_indirect(r1, c1)
