@@ -291,9 +291,10 @@ int  trq_gather_status(trq_gather* g);
 int  trq_gather_destroy(trq_gather* g);
 
 /* Per-kernel timing for roofline reports: when enabled, every device-pointer trq_trace records CUDA
- * events (on the caller's stream) around the traversal kernel and around the resolve kernel.
- * trq_profile_read waits for them and returns the SUMS over the launches since the last read
- * (at most the 64 most recent) and resets. Not for TRQ_HOST_PTRS calls. */
+ * events (on the caller's stream) around the traversal kernel (with its ordering passes, if any) and
+ * around what follows it -- the resolve pass of TRQ_KERNEL_REFLAYOUT; the packed kernel finishes its own
+ * records, so resolveKernelMs is 0 for it. trq_profile_read waits for the events and returns the SUMS over
+ * the launches since the last read (at most the 64 most recent) and resets. Not for TRQ_HOST_PTRS calls. */
 int  trq_profile_enable(trq_scene* scene, int on);
 int  trq_profile_read(trq_scene* scene, uint32_t* nLaunches, float* traceKernelMs, float* resolveKernelMs);
 
