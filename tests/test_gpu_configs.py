@@ -46,10 +46,11 @@ def test_every_configuration_matches_the_oracle(built, port):
                     assert_hits_equal(gpu_trace(scene, rays, any_hit), want, f"cfg {name}")
         scene.close()
     assert staged_any
-    # the library's own choice: staging for small trees only
-    small, big = Scene(mixed, 0), Scene(soup, 0)
-    assert small.set_kernel_config(-1) > 0 and big.set_kernel_config(-1) == 0
-    small.close(); big.close()
+    # the library's own choice: staging only for trees that fit into the staged block whole
+    small, mid, big = Scene(H.scene_c1(), 0), Scene(mixed, 0), Scene(soup, 0)
+    assert small.set_kernel_config(-1) == small.info["nInterior"] and "top=true" in small.kernel_config()
+    assert mid.set_kernel_config(-1) == 0 and big.set_kernel_config(-1) == 0 and "top=false" in big.kernel_config()
+    small.close(); mid.close(); big.close()
 
 
 def test_hit16_is_the_packed_form_of_trq_hit(built, port):

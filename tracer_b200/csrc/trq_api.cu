@@ -625,11 +625,12 @@ int finish_scene(trq_scene* s, const trq_scene_desc* d, trq_scene_info_t info, u
     }
     if (!s->cfg[0].usable) return trq::fail(TRQ_ERR_CUDA, "trace_packed_kernel does not fit on an SM (smem %zu)", s->cfg[0].smem);
     TRQ_LAP(tm, "kernel configurations");
-    // Staging the top of the tree pays when the staged block is a large share of the tree (C1 +15 %, C2 +2-3 %) and loses on
-    // 1 M+ triangle scenes (profiles/r02_top_of_tree_experiment.txt): chosen for small trees only.
+    // Staging pays when the staged block IS the tree (C1: +2-15 %); with the leaf-specialised kernels it no longer does when
+    // only the top levels fit (C2 / the reference's Cornell mix: -3 to -6 %), and it loses clearly on 1 M+ triangle scenes
+    // (profiles/r02_top_of_tree_experiment.txt): chosen only for trees that fit whole.
     s->autoCfg = 0;
     for (int c = 1; c < kNumCfgs; ++c)
-        if (kCfgs[c].top && s->cfg[c].usable && (uint64_t)info.nInterior <= 16ull * s->cfg[c].topCount) { s->autoCfg = c; break; }
+        if (kCfgs[c].top && s->cfg[c].usable && info.nInterior <= s->cfg[c].topCount) { s->autoCfg = c; break; }
     s->defaultCfg = s->autoCfg;
 
     info.bytesReferenceLayout = (uint64_t)d->nSphere * sizeof(RefSphere) + (uint64_t)d->nSquare * sizeof(RefSquare) +
