@@ -683,6 +683,11 @@ def run_gpu_arm(a):
         e2e_extra["e2e_hit16"] = {"value": round(total_rays * e2e_steps / s16 / 1e6, 2), "unit": UNIT, "h2d_bytes_per_step": int(n * 32),
                                   "d2h_bytes_per_step": int(n * 16), "steps": e2e_steps,
                                   "equals_packed_device_records": bool(np.array_equal(h_hits16.numpy().view(np.uint8).reshape(-1), want16.view(np.uint8).reshape(-1)))}
+        if a.workload == "c5" and sort:
+            # the same host-pointer call WITHOUT the caller's ordering hint (the library examines each 1 M-ray chunk itself)
+            su = wall(lambda: scene.hit_host(h_rays.data_ptr(), n, h_hits.data_ptr(), any=any_hit, sort=False), e2e_steps)
+            e2e_extra["e2e_unhinted"] = {"value": round(total_rays * e2e_steps / su / 1e6, 2), "unit": UNIT, "steps": e2e_steps,
+                                         "equals_device_path": bool(torch.equal(h_hits.view(torch.int32), d_hits_ref.cpu().view(torch.int32)))}
         # same traffic as e2e, but the K calls are queued back to back (TRQ_HOST_ASYNC, two alternating pinned result
         # buffers) so that one call's D2H overlaps the next call's H2D; collected once at the end
         h_hits2 = torch.empty((n, 8), dtype=torch.float32).pin_memory()

@@ -466,7 +466,9 @@ int trace_host(trq_scene* s, const trq_ray* rays, uint64_t n, uint32_t flags, vo
     const size_t recBytes = (flags & TRQ_HIT16) ? sizeof(trq_hit16) : sizeof(trq_hit);
     std::lock_guard<std::mutex> lock(s->stageMutex);
     // a sorted chunk is only as coherent as it is large: C5 e2e 461 / 605 / 599 / 504 Mrays/s at 512K / 1M / 2M / 4M rays
-    const uint64_t want = (flags & TRQ_SORT_RAYS) ? 2 * chunkRays : chunkRays;
+    // (the same chunk size for a tree much larger than L2 without the hint: the automatic mode looks at batches of >= 2^20 rays)
+    const bool mayOrder = (flags & TRQ_SORT_RAYS) || (s->largeTree && !(flags & TRQ_NO_SORT));
+    const uint64_t want = mayOrder ? 2 * chunkRays : chunkRays;
     const uint64_t chunk = n < want ? n : want;
     int rc = ensure_staging(s, chunk);
     if (rc != TRQ_OK) return rc;
